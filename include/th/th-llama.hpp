@@ -1,0 +1,133 @@
+// th-llama.hpp -- LLaMA model graph on the th:: op surface (mirrors kayvr/token-hawk th-llama.hpp).
+// Same structs and entry points; two evaluation paths behind th_eval_gpu:
+//   EvalPath_OpGraph : the reference's own graph, op for op (build_layer_cmdbuf, th-llama.cpp:270-452)
+//   EvalPath_Fused   : one persistent sm_100a kernel per token (thk_decoder_step) -- the default
+#pragma once
+
+#include <array>
+#include <functional>
+#include <memory>
+#include <random>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "th/th.hpp"
+
+namespace th {
+
+static const bool kSplitFinalMultiply = false;   // no 256 MB buffer cap on CUDA (th-llama.hpp:20, th.cpp:3793)
+static const bool kUseGpuEmbeddingSelection = true;   // embedding row gathered on the device (th-llama.hpp:21)
+
+typedef int tk_llama_token;
+
+enum EvalPath { EvalPath_Fused = 0, EvalPath_OpGraph = 1 };
+
+struct LlamaLayer {            // th-llama.hpp:37-55
+    int64_t index{};
+    TensorBuffer attention_norm{};
+    TensorBuffer wq{}, wk{}, wv{}, wo{};
+    TensorBuffer ffn_norm{};
+    TensorBuffer w1{}, w2{}, w3{};
+    TensorBuffer key_cache{};      // [n_ctx][n_head][head_dim] f32 -- op-graph path (reference layout)
+    TensorBuffer value_cache{};
+    TensorBuffer key_cache_hpd{};  // [n_head][n_ctx][head_dim] f32 -- fused path (no per-token transposes)
+    TensorBuffer value_cache_hpd{};
+};
+
+struct LlamaLayerComputePipeline {   // th-llama.hpp:57-78
+    ComputePipeline p01{true}, p02{true}, p03_mm{true}, p03_mm_reduce{true}, p04_rope{true}, p05_trans{true},
+        p06_mm{true}, p07_softmax{true}, p08_mm{true}, p09_t{true}, p10_mm{true}, p10_mm_reduce{true}, p11_add{true},
+        p12_rms{true}, p13_norm{true}, p14_mm{true}, p15_silu{true}, p16_hadamard{true}, p17_mm{true}, p18_add{true};
+};
+struct LlamaFinalComputePipeline {   // th-llama.hpp:80-85
+    ComputePipeline p01{true}, p02{true}, p03{true}, p03_reduce{true};
+};
+
+struct LlamaVocab {                  // th-llama.hpp:87-98
+    using id = int32_t;
+    using token = std::string;
+    struct token_score { token tok; float score; };
+    std::unordered_map<token, id> token_to_id;
+    std::vector<token_score> id_to_token;
+};
+
+struct LlamaModel {                  // th-llama.hpp:100-177
+    std::mt19937 rng{};
+    int32_t n_vocab = 32000, n_ctx = 512, n_embd = 4096, n_mult = 256, n_head = 32, n_layer = 32, n_rot = 64;
+    int32_t n_batch = 8;
+    int32_t f16 = 1;
+    int32_t n_ff = 11008;            // derived at load (th-llama-loader.cpp:349); no 11008 assert here
+
+    TensorBuffer tok_embeddings{};   // f16 on the device (the reference keeps an f32 CPU copy)
+    std::vector<LlamaLayer> layers{};
+    LlamaLayerComputePipeline ps{}, pb{};
+    LlamaFinalComputePipeline pfs{}, pfb{};
+    TensorBuffer norm{};
+    TensorBuffer outputMat{};
+    TensorBuffer out{};
+    TensorBuffer outScratch{};
+    static const int nInpBuffers = 7;
+    TensorBuffer inp[nInpBuffers]{};
+    TensorBuffer ffWorking[2]{};
+    TensorBuffer working_key_cache{};
+    TensorBuffer working_val_cache{};
+    TensorBuffer resultBuffer{};     // cpuBackup only: pinned host staging for the logits
+    WGPUBuffer networkUniforms{};
+    std::array<WGPUBuffer, 5> dimsUniforms{};
+    LlamaVocab vocab{};
+
+    std::function<void(std::string, std::string)> onNewToken;
+    std::function<void(std::string)> onInferenceComplete;
+    std::function<void(std::string)> onError;
+
+    bool loadFailed = false;
+    std::unordered_map<std::string, TensorBuffer> loadedMapping;
+
+    std::vector<tk_llama_token> embd_inp{}, embd{};
+    int n_past = 0;
+    int n_consumed = 0;
+    tk_llama_token lastGeneratedToken{};
+    std::string generatedMessage;
+    std::vector<tk_llama_token> last_n_tokens{};
+
+    // ---- CUDA engine state (no reference analogue) ----
+    WGPUDevice device{};
+    EvalPath evalPath = EvalPath_Fused;
+    float samplerTemp = 0.0f;        // reference hard-codes 0.8 (th-llama.cpp:721); greedy is the parity mode
+    thk_decoder* decoder = nullptr;
+    int32_t* d_token = nullptr;      // device: token id in, greedy id out
+    int32_t* d_next = nullptr;
+    float* pinnedLogits = nullptr;
+    std::vector<float> lastLogits;
+    int64_t gpuLaunches = 0;         // kernels launched by the last th_eval_gpu call
+
+    ~LlamaModel();
+};
+
+static const size_t kLlamaUniformsSize = 32;
+typedef thk_network_uniforms LlamaNetworkUniforms;    // th-llama.hpp:181-192
+typedef thk_dims_uniforms LlamaTensorDimsUniforms;    // th-llama.hpp:195-204
+static_assert(sizeof(LlamaNetworkUniforms) == kLlamaUniformsSize, "uniform block must be 32 bytes");
+static_assert(sizeof(LlamaTensorDimsUniforms) == kLlamaUniformsSize, "uniform block must be 32 bytes");
+
+void reset_layer_tensors(LlamaLayer& layer);
+void reset_working_memory_tensors(LlamaModel& m);
+void build_pipelines_llama(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m);
+void build_layer_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, std::shared_ptr<LlamaModel> m, LlamaLayer& l,
+                        LlamaLayerComputePipeline& p, int n_tokens, int n_past);
+void build_final_compute_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, std::shared_ptr<LlamaModel> m,
+                                LlamaFinalComputePipeline& p, int n_tokens);
+// th-llama.cpp:464-660.  Returns the sampled token (greedy), or -1 on error.  n_tokens > 1 is
+// evaluated as n_tokens consecutive single-token steps (logits of the last one are kept).
+tk_llama_token th_eval_gpu(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens,
+                           int n_tokens, int n_past);
+// greedy branch of th-llama.cpp:814-838
+tk_llama_token llama_sample_top_p_top_k(std::shared_ptr<LlamaModel> m, const std::vector<tk_llama_token>& last_n_tokens, int top_k,
+                                        float top_p, float temp, float repeat_penalty, std::vector<float>& logits);
+// n_new greedy tokens after feeding `prompt` one token at a time (do_inference's sync loop,
+// th-llama.cpp:199-238, without tokenizer / printing)
+std::vector<tk_llama_token> generate_greedy(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m,
+                                            const std::vector<tk_llama_token>& prompt, int n_new);
+
+}  // namespace th

@@ -1,0 +1,270 @@
+// th_llama.cpp -- LLaMA graph on the th:: op surface (mirrors kayvr/token-hawk th-llama.cpp).
+//
+// Two ways to evaluate a token behind the same th_eval_gpu entry point:
+//   * EvalPath_OpGraph: the reference's graph, one op per launch, in the reference's order and with
+//     its buffer roles (build_layer_cmdbuf th-llama.cpp:270-452, build_final_compute_cmdbuf :240-268).
+//     It exists to show the op surface is a drop-in and as a second, independent GPU path for parity.
+//   * EvalPath_Fused: thk_decoder_step -- one persistent sm_100a kernel per token (default).
+#include "th/th-llama.hpp"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <utility>
+
+namespace th {
+
+extern int64_t g_launch_count;   // th.cpp: launches issued through emit()
+
+static EncoderTag* const kEncoder = reinterpret_cast<EncoderTag*>(1);   // "a submission is open"
+
+LlamaModel::~LlamaModel() {
+    if (decoder) thk_decoder_destroy(decoder);
+    if (device) {
+        if (d_token) thk_free(device, d_token);
+        if (d_next) thk_free(device, d_next);
+        if (networkUniforms) thk_free(device, networkUniforms);
+        for (auto& u : dimsUniforms) if (u) thk_free(device, u);
+        if (pinnedLogits) thk_host_free(device, pinnedLogits);
+    }
+}
+
+void reset_layer_tensors(LlamaLayer& l) {   // th-llama.cpp:78-93
+    l.attention_norm.reset_shape();
+    l.wq.reset_shape(); l.wk.reset_shape(); l.wv.reset_shape(); l.wo.reset_shape();
+    l.ffn_norm.reset_shape();
+    l.w1.reset_shape(); l.w2.reset_shape(); l.w3.reset_shape();
+    l.key_cache.reset_shape(); l.value_cache.reset_shape();
+}
+
+void reset_working_memory_tensors(LlamaModel& m) {   // th-llama.cpp:95-106
+    m.working_key_cache.reset_shape();
+    m.working_val_cache.reset_shape();
+    for (int i = 0; i < LlamaModel::nInpBuffers; ++i) m.inp[i].reset_shape();
+    m.ffWorking[0].reset_shape();
+    m.ffWorking[1].reset_shape();
+}
+
+// Dry run with a null encoder: every op site only records its shape contract (th-llama.cpp:66-76).
+// Only the single-token sets are built; the 8-token sets of the reference feed a dormant path.
+void build_pipelines_llama(WGPUDevice device, WGPUQueue, std::shared_ptr<LlamaModel> m) {
+    LlamaLayer& l = m->layers[0];
+    build_layer_cmdbuf(device, nullptr, m, l, m->ps, 1, 0);
+    build_final_compute_cmdbuf(device, nullptr, m, m->pfs, 1);
+    reset_working_memory_tensors(*m);
+    reset_layer_tensors(l);
+}
+
+// th-llama.cpp:240-268.  No output split and no reduce: one [n_vocab, n_embd] matvec.
+void build_final_compute_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, std::shared_ptr<LlamaModel> m,
+                                LlamaFinalComputePipeline& p, int n_tokens) {
+    reset_working_memory_tensors(*m);
+    m->inp[0].shape = TensorShape{0, 0, n_tokens, m->n_embd};
+    cmdbuf_rms_norm(device, encoder, nullptr, &p.p01, m->inp[0]);
+    cmdbuf_row_element_multiply(device, encoder, nullptr, &p.p02, m->inp[0], m->norm);
+    // last row only (aOffset), th-llama.cpp:265-266
+    const int64_t aOffset = ((m->inp[0].shape.r - 1) * m->inp[0].shape.c) * (int64_t)get_TensorType_size(m->inp[0].type);
+    TensorBuffer& x = m->inp[0];
+    const TensorShape keep = x.shape;
+    x.shape = TensorShape{0, 0, 1, m->n_embd};   // the matvec sees one row; the offset selects which
+    cmdbuf_vector_mat_mul_trans(device, encoder, nullptr, &p.p03, x, m->outputMat, m->out, aOffset);
+    x.shape = keep;
+}
+
+// th-llama.cpp:270-452, n_tokens == 1 branch.  Buffer roles as in the reference: inp0 = x (normed in
+// place), inp6 = residual copy, inp1..3 = Q/K/V, inp4 = Q^T, inp5 = scores.
+void build_layer_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, std::shared_ptr<LlamaModel> m, LlamaLayer& l,
+                        LlamaLayerComputePipeline& p, int n_tokens, int n_past) {
+    reset_working_memory_tensors(*m);
+    reset_layer_tensors(l);
+    if (n_tokens != 1) { fprintf(stderr, "build_layer_cmdbuf: the op graph evaluates one token at a time\n"); return; }
+
+    TensorBuffer& queryBuf = m->inp[1];
+    TensorBuffer& keyBuf = m->inp[2];
+    TensorBuffer& valueBuf = m->inp[3];
+    TensorBuffer& queryTranspose = m->inp[4];
+    const int n_embd = m->n_embd, n_head = m->n_head, hd = n_embd / n_head;
+
+    for (TensorBuffer* t : {&m->inp[0], &queryBuf, &keyBuf, &valueBuf, &queryTranspose, &m->inp[6]}) t->shape = TensorShape{0, 0, n_tokens, n_embd};
+
+    cmdbuf_rms_norm(device, encoder, nullptr, &p.p01, m->inp[0]);                                   // :299
+    cmdbuf_row_element_multiply(device, encoder, nullptr, &p.p02, m->inp[0], l.attention_norm);     // :300
+    cmdbuf_vector_mat_mul_trans(device, encoder, nullptr, &p.p03_mm, m->inp[0], l.wq, queryBuf, 0); // :304
+    cmdbuf_vector_mat_mul_trans(device, encoder, nullptr, &p.p03_mm, m->inp[0], l.wk, keyBuf, 0);   // :305
+    cmdbuf_vector_mat_mul_trans(device, encoder, nullptr, &p.p03_mm, m->inp[0], l.wv, valueBuf, 0); // :306
+
+    queryBuf.shape = TensorShape{0, n_tokens, n_head, hd};                                          // :317-319
+    keyBuf.shape = TensorShape{0, n_tokens, n_head, hd};
+    valueBuf.shape = TensorShape{0, n_head, n_tokens, hd};
+    cmdbuf_RoPE(device, encoder, nullptr, &p.p04_rope, queryBuf, m->networkUniforms);               // :321
+    cmdbuf_RoPE(device, encoder, nullptr, &p.p04_rope, keyBuf, m->networkUniforms);                 // :322
+
+    if (encoder) {   // KV append, :332-339
+        const size_t off = (size_t)n_past * n_embd * sizeof(float);
+        thk_copy(device, l.key_cache.gpu, off, keyBuf.gpu, 0, keyBuf.get_size_bytes());
+        thk_copy(device, l.value_cache.gpu, off, valueBuf.gpu, 0, valueBuf.get_size_bytes());
+    }
+
+    l.key_cache.shape.b = n_past + n_tokens;                                                        // :341-350
+    m->working_key_cache.shape = l.key_cache.shape;
+    std::swap(m->working_key_cache.shape.b, m->working_key_cache.shape.r);
+    l.value_cache.shape.b = n_past + n_tokens;
+    m->working_val_cache.shape = l.value_cache.shape;
+    std::swap(m->working_val_cache.shape.b, m->working_val_cache.shape.r);
+    queryTranspose.shape = queryBuf.shape;
+    std::swap(queryTranspose.shape.b, queryTranspose.shape.r);
+
+    cmdbuf_transpose(device, encoder, nullptr, &p.p05_trans, l.key_cache, m->working_key_cache, true, m->dimsUniforms[0]);   // :353
+    cmdbuf_transpose(device, encoder, nullptr, &p.p05_trans, l.value_cache, m->working_val_cache, true, m->dimsUniforms[0]); // :354
+    cmdbuf_transpose(device, encoder, nullptr, &p.p05_trans, queryBuf, queryTranspose, true, m->dimsUniforms[1]);            // :355
+
+    std::swap(m->working_key_cache.shape.r, m->working_key_cache.shape.c);                          // :361
+    m->inp[5].shape = TensorShape{0, n_head, n_tokens, n_tokens + n_past};
+    cmdbuf_mat_mul(device, encoder, nullptr, &p.p06_mm, queryTranspose, m->working_key_cache, m->inp[5], 1, m->dimsUniforms[2]); // :365
+    cmdbuf_row_softmax(device, encoder, nullptr, &p.p07_softmax, m->inp[5], m->dimsUniforms[3]);    // :373
+
+    keyBuf.shape = TensorShape{0, n_head, n_tokens, hd};
+    cmdbuf_mat_mul(device, encoder, nullptr, &p.p08_mm, m->inp[5], m->working_val_cache, keyBuf, 0, m->dimsUniforms[4]);     // :380
+
+    std::swap(valueBuf.shape.b, valueBuf.shape.r);                                                  // :396
+    cmdbuf_transpose(device, encoder, nullptr, &p.p09_t, keyBuf, valueBuf, true, nullptr);          // :397
+
+    valueBuf.shape = TensorShape{0, 0, n_tokens, n_embd};
+    m->inp[1].shape = TensorShape{0, 0, n_tokens, n_embd};
+    cmdbuf_vector_mat_mul_trans(device, encoder, nullptr, &p.p10_mm, valueBuf, l.wo, m->inp[1], 0); // :402
+
+    m->inp[6].shape = m->inp[1].shape;
+    m->inp[2].shape = m->inp[1].shape;
+    cmdbuf_addition(device, encoder, nullptr, &p.p11_add, m->inp[1], m->inp[6], m->inp[2]);         // :409
+    if (encoder) thk_copy(device, m->inp[3].gpu, 0, m->inp[2].gpu, 0, m->inp[2].get_size_bytes());  // :412
+
+    cmdbuf_rms_norm(device, encoder, nullptr, &p.p12_rms, m->inp[2]);                               // :415
+    cmdbuf_row_element_multiply(device, encoder, nullptr, &p.p13_norm, m->inp[2], l.ffn_norm);      // :416
+
+    m->ffWorking[0].shape.r = n_tokens;
+    m->ffWorking[1].shape.r = n_tokens;
+    cmdbuf_vector_mat_mul_trans(device, encoder, nullptr, &p.p14_mm, m->inp[2], l.w1, m->ffWorking[0], 0);  // :423
+    cmdbuf_vector_mat_mul_trans(device, encoder, nullptr, &p.p14_mm, m->inp[2], l.w3, m->ffWorking[1], 0);  // :424
+    cmdbuf_silu(device, encoder, nullptr, &p.p15_silu, m->ffWorking[0]);                            // :436
+    cmdbuf_element_mult_in_place(device, encoder, nullptr, &p.p16_hadamard, m->ffWorking[0], m->ffWorking[1]); // :438
+    cmdbuf_vector_mat_mul_trans(device, encoder, nullptr, &p.p17_mm, m->ffWorking[0], l.w2, m->inp[2], 0);  // :441
+
+    m->inp[3].shape = m->inp[2].shape;
+    m->inp[0].shape = m->inp[2].shape;
+    cmdbuf_addition(device, encoder, nullptr, &p.p18_add, m->inp[3], m->inp[2], m->inp[0]);         // :447
+    if (encoder) thk_copy(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, m->inp[0].get_size_bytes());  // :450
+}
+
+// greedy branch of th-llama.cpp:814-838; other temperatures are outside the hot path
+tk_llama_token llama_sample_top_p_top_k(std::shared_ptr<LlamaModel> m, const std::vector<tk_llama_token>&, int, float, float temp,
+                                        float, std::vector<float>& logits) {
+    const int n_logits = m->n_vocab;
+    if ((int)logits.size() < n_logits) return -1;
+    const float* pl = logits.data() + logits.size() - n_logits;
+    if (temp > 0) {
+        fprintf(stderr, "llama_sample_top_p_top_k: only the greedy branch (temp <= 0) is implemented\n");
+        return -1;
+    }
+    float max_logit = pl[0];
+    tk_llama_token max_id = 0;
+    for (int i = 1; i < n_logits; ++i)
+        if (pl[i] > max_logit) { max_logit = pl[i]; max_id = i; }
+    return max_id;
+}
+
+static bool write_uniforms(WGPUQueue queue, std::shared_ptr<LlamaModel> m, int n_tokens, int n_past) {
+    // th-llama.cpp:479-550
+    const uint32_t H = m->n_head, D = m->n_embd / m->n_head, Np = (uint32_t)(n_past + n_tokens);
+    LlamaNetworkUniforms nu{};
+    nu.n_past = (uint32_t)n_past; nu.n_tokens = (uint32_t)n_tokens;
+    LlamaTensorDimsUniforms d[5]{};
+    d[0].A_B = Np ? Np : 1; d[0].A_M = H; d[0].A_N = D;                                                   // cache transpose
+    d[1].A_B = (uint32_t)n_tokens; d[1].A_M = H; d[1].A_N = D;                                          // q transpose
+    d[2].A_B = H; d[2].A_M = (uint32_t)n_tokens; d[2].A_N = D; d[2].scale = 1.0f / sqrtf((float)D);
+    d[2].B_B = H; d[2].B_M = D; d[2].B_N = Np;                                                           // QK^T
+    d[3].A_B = H; d[3].A_M = (uint32_t)n_tokens; d[3].A_N = Np;                                          // softmax
+    d[4].A_B = H; d[4].A_M = (uint32_t)n_tokens; d[4].A_N = Np; d[4].scale = 1.0f;
+    d[4].B_B = H; d[4].B_M = Np; d[4].B_N = D;                                                           // PV
+    if (thk_upload(queue, m->networkUniforms, 0, &nu, kLlamaUniformsSize)) return false;
+    for (int i = 0; i < 5; ++i)
+        if (thk_upload(queue, m->dimsUniforms[i], 0, &d[i], kLlamaUniformsSize)) return false;
+    return true;
+}
+
+static bool eval_one_opgraph(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, tk_llama_token token, int n_past) {
+    if (!write_uniforms(queue, m, 1, n_past)) return false;
+    // embedding row -> inp0 and inp6 on the device (the kUseGpuEmbeddingSelection branch, th-llama.cpp:552-575)
+    reset_working_memory_tensors(*m);
+    m->inp[0].shape = TensorShape{0, 0, 1, m->n_embd};
+    m->inp[6].shape = m->inp[0].shape;
+    const int64_t stride = m->tok_embeddings.shape.c * (int64_t)get_TensorType_size(m->tok_embeddings.type);
+    TensorBuffer& emb = m->tok_embeddings;
+    const TensorShape keep = emb.shape;
+    emb.shape = TensorShape{0, 0, 1, m->n_embd};
+    CommandBuffer cb = cmdbuf_f16_f32_conversion(device, kEncoder, nullptr, nullptr, m->inp[0], emb, 4, 0, (int)(stride * token));
+    emb.shape = keep;
+    if (!cb.is_valid()) return false;
+    thk_copy(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, m->inp[0].get_size_bytes());
+    for (auto& l : m->layers) build_layer_cmdbuf(device, kEncoder, m, l, m->ps, 1, n_past);   // :596-618
+    reset_working_memory_tensors(*m);
+    build_final_compute_cmdbuf(device, kEncoder, m, m->pfs, 1);                               // :632
+    return true;
+}
+
+tk_llama_token th_eval_gpu(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens,
+                           int n_tokens, int n_past) {
+    if (!m || !tokens || n_tokens < 1) { fprintf(stderr, "th_eval_gpu: bad arguments\n"); return -1; }
+    if (n_past < 0 || n_past + n_tokens > m->n_ctx) {
+        fprintf(stderr, "th_eval_gpu: n_past %d + n_tokens %d exceeds the context (%d)\n", n_past, n_tokens, m->n_ctx);
+        if (m->onError) m->onError("context full");
+        return -1;
+    }
+    const int64_t launches0 = g_launch_count;
+    int64_t fused_launches = 0;
+    for (int i = 0; i < n_tokens; ++i) {
+        const tk_llama_token tok = tokens[i];
+        if (tok < 0 || tok >= m->n_vocab) { fprintf(stderr, "th_eval_gpu: token %d outside the vocabulary\n", tok); return -1; }
+        if (m->evalPath == EvalPath_Fused) {
+            if (!m->decoder) { fprintf(stderr, "th_eval_gpu: fused decoder missing\n"); return -1; }
+            if (thk_upload(queue, m->d_token, 0, &tok, sizeof(int32_t))) { fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error()); return -1; }
+            if (thk_decoder_step(m->decoder, m->d_token, n_past + i, (float*)m->out.gpu, m->d_next, nullptr)) {
+                fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error());
+                return -1;
+            }
+            fused_launches += 1;
+        } else {
+            if (!eval_one_opgraph(device, queue, m, tok, n_past + i)) { fprintf(stderr, "th_eval_gpu: op graph failed\n"); return -1; }
+        }
+    }
+    // logits -> pinned host buffer (resultBuffer + map, th-llama.cpp:646-706), then sample on the host
+    if (thk_download(queue, m->pinnedLogits, m->out.gpu, 0, (size_t)m->n_vocab * sizeof(float))) {
+        fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error());
+        return -1;
+    }
+    if (m->evalPath == EvalPath_Fused && thk_decoder_check(m->decoder)) { fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error()); return -1; }
+    m->gpuLaunches = (g_launch_count - launches0) + fused_launches;
+    m->lastLogits.assign(m->pinnedLogits, m->pinnedLogits + m->n_vocab);
+    return llama_sample_top_p_top_k(m, {}, 40, 0.95f, m->samplerTemp, 1.10f, m->lastLogits);
+}
+
+std::vector<tk_llama_token> generate_greedy(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m,
+                                            const std::vector<tk_llama_token>& prompt, int n_new) {
+    std::vector<tk_llama_token> out;
+    tk_llama_token tok = -1;
+    for (tk_llama_token t : prompt) {            // prompt is consumed one token per evaluation (kAllowedSubsequentBatchSize = 1)
+        tok = th_eval_gpu(device, queue, m, &t, 1, m->n_past);
+        if (tok < 0) return out;
+        m->n_past += 1;
+    }
+    for (int i = 0; i < n_new && tok >= 0; ++i) {
+        out.push_back(tok);
+        m->lastGeneratedToken = tok;
+        if (m->n_past >= m->n_ctx) break;
+        tok = th_eval_gpu(device, queue, m, &tok, 1, m->n_past);
+        m->n_past += 1;
+    }
+    return out;
+}
+
+}  // namespace th

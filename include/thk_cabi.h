@@ -169,6 +169,10 @@ int thk_decoder_last_launches(thk_decoder* dec);
 /* blocks on the stream and reports an in-kernel abort (watchdog on a barrier wait -> THK_E_TIMEOUT,
  * token id out of range -> THK_E_INVALID); the reference's validators assert instead (th-llama.cpp:606) */
 int thk_decoder_check(thk_decoder* dec);
+/* phase profile (no reference analogue; the reference only has wall-clock stats, th.cpp:45-87): when
+ * enabled, CTA 0 stores %globaltimer (ns) at kernel start [0] and after grid barrier k [k]; host_out
+ * (may be NULL) receives the first n entries of the last launch. */
+int thk_decoder_profile(thk_decoder* dec, int enable, unsigned long long* host_out, int n);
 /* tensor-parallel wiring: peer pointers obtained by the host via CUDA IPC (or same-process P2P).
  * peer_bufs[r] / peer_flags[r] are device-visible addresses of rank r's exchange buffer / flag
  * array as returned by thk_decoder_exchange_info on that rank. */

@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIBDIR = os.path.join(_PKG, "lib")
+_LIBDIR = os.path.join(_PKG, os.environ.get("THK_LIBDIR", "lib"))   # lib8/ etc. hold kernel variants for A/B runs
 KERNEL_LIB = os.path.join(_LIBDIR, "libthk_sm100a.so")
 HOST_LIB = os.path.join(_LIBDIR, "libth_b200.so")
 
@@ -86,6 +86,7 @@ def kernels() -> C.CDLL:
             "thk_decoder_hidden": [vp, C.POINTER(vp)],
             "thk_decoder_last_launches": [vp],
             "thk_decoder_check": [vp],
+            "thk_decoder_profile": [vp, C.c_int, C.POINTER(C.c_uint64), C.c_int],
             "thk_decoder_exchange_info": [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t)],
             "thk_decoder_set_peers": [vp, C.POINTER(vp), C.POINTER(vp), C.c_int],
             "thk_gemm_f16_tc": [vp, vp, vp, vp, i64, i64, i64],
@@ -131,6 +132,7 @@ def host() -> C.CDLL:
         H.capi_stream.restype = vp
         H.capi_stream.argtypes = [vp]
         H.capi_fill_kv.argtypes = [vp, u64, C.c_int]
+        H.capi_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.c_int]
         H.capi_hidden.argtypes = [vp, f32p]
         H.capi_tensor_info.restype = i64
         H.capi_tensor_info.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
@@ -304,6 +306,19 @@ class LlamaModel:
         if host().capi_tensor_download(self.h, name.encode(), out.ctypes.data_as(vp), nbytes):
             raise ThkError(-1, host().capi_last_error().decode())
         return out
+
+    def profile(self, enable: bool, fetch: bool = False):
+        """In-kernel timeline of the last fused launch.  Returns (marks[cta][phase<256][8] ns, producer[cta][4])
+        when fetch is set; slots: 0 phase start, 1 prologue end, 2 first tile ready, 3 last tile done,
+        4 barrier arrive, 5 after fence, 6 consumer ring-wait cycles."""
+        grid = self.dev.sm_count
+        n = grid * 256 * 8 + grid * 4 if fetch else 0
+        buf = np.zeros(max(n, 1), dtype=np.uint64)
+        if host().capi_profile(self.h, int(enable), buf.ctypes.data_as(C.POINTER(C.c_uint64)) if fetch else None, n):
+            raise ThkError(-1, host().capi_last_error().decode())
+        if not fetch:
+            return None
+        return buf[:grid * 256 * 8].reshape(grid, 256, 8).astype(np.int64), buf[grid * 256 * 8:].reshape(grid, 4).astype(np.int64)
 
     # enqueue-only calls for stream timing
     def set_token(self, tok: int):

@@ -16,7 +16,7 @@
 //
 // Arithmetic follows oracle/th_oracle.c (the restatement of the WGSL); only summation order
 // differs.  No tensor cores: at M=1 the work is 1 FLOP/byte and HBM-bound.
-#include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -24,14 +24,33 @@ namespace {
 
 constexpr int kSlotBytes = 32 * 1024;
 constexpr int kNumSlots = 5;
-constexpr int kConsumerWarps = 8;
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = 32 + kConsumerThreads;
+#ifndef THK_MATH_WARPS
+#define THK_MATH_WARPS 8
+#endif
+constexpr int kMathWarps = THK_MATH_WARPS;            // 8 or 16
+constexpr int kRC = 64 / kMathWarps;                  // (rows per warp) x (256-col chunks per warp) per 32 KB tile
+constexpr int kMathThreads = kMathWarps * 32;
+constexpr int kMathBase = 32;                         // warp 0 = producer, warps 1..8 = math, warp 9 = epilogue
+constexpr int kThreads = kMathBase + kMathThreads + 32;
+constexpr int kConsumerWarps = kMathWarps;
+enum NamedBarrier { BAR_ALL = 1, BAR_MATH = 2, BAR_A0 = 3, BAR_A1 = 4, BAR_B0 = 5, BAR_B1 = 6 };
 constexpr int kMaxTilePos = 128;     // attention: positions per tile cap (score staging size)
 constexpr int kMaxHeadDim = 128;
 constexpr int kMaxGroupRows = 64;    // RT <= 64
 
 struct MatCfg { int WC, RPW, CPW; };   // col-warps, rows per warp, 256-col chunks per warp per tile
+
+// Host-computed tile schedule of one matvec phase (no integer divisions on the device's critical path)
+struct PhaseDesc {
+    int C;            // columns (input dimension)
+    int WC, RPW, CPW; // col-warps, rows per warp, 256-col chunks per warp per tile
+    int RT, CT, KT;   // rows per group, columns per K tile, K tiles per group
+    int nseg, paired; // segments (weight matrices) and whether seg0/seg1 rows are processed pairwise
+    int rows[3];      // rows per segment
+    int gs[3];        // row groups per segment
+    int G;            // row groups in the phase (paired: groups of seg0)
+};
+enum PhaseKind { PH_QKV = 0, PH_WO = 1, PH_W13 = 2, PH_W2 = 3, PH_OUT = 4 };
 
 struct DecParams {
     int n_vocab, n_embd, n_head, n_layer, n_ff, n_ctx, head_dim;
@@ -52,13 +71,13 @@ struct DecParams {
     float* logits;
     int* next_token;
     float* next_logit;
-    MatCfg cfg_qkv, cfg_wo, cfg_w13, cfg_w2, cfg_out;
+    PhaseDesc ph[5];
     int att_tpos;                       // positions per attention tile
     int att_max_split;
     unsigned long long timeout_ns;
+    unsigned long long* prof;           // optional timeline: [cta][phase<256][8] u64 (see prof_mark), then [cta][4] producer stats
 };
 
-struct Seg { const uint16_t* W; int rows; };
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -104,7 +123,11 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+constexpr int kProfPhases = 256;
+enum ProfSlot { PROF_START = 0, PROF_PROLOGUE = 1, PROF_FIRST_TILE = 2, PROF_LAST_TILE = 3, PROF_ARRIVE = 4, PROF_FENCED = 5, PROF_WAIT_FULL = 6 };
 
 __device__ __forceinline__ bool aborted(const DecParams& p) { return ld_volatile_u32(p.status) != 0; }
 __device__ __noinline__ void raise_abort(const DecParams& p, unsigned code, unsigned a, unsigned b) {
@@ -136,8 +159,7 @@ struct SmemMisc {
     alignas(16) float redo[kConsumerWarps][kMaxHeadDim];
     float redl[kConsumerWarps];
     float norm_part[kConsumerWarps];
-    float bval[kMaxGroupRows];
-    int bidx[kMaxGroupRows];
+    float2 rope[kMaxHeadDim / 2];       // (cos, sin) of n_past * theta_i for this token
     int flag;
 };
 
@@ -149,34 +171,17 @@ __device__ __forceinline__ int xs_index(int col) {
 }
 
 // ------------------------------------------------------------------------------------------
-// tile schedule of one matvec phase for this CTA (shared by producer and consumers)
+// this CTA's share of a phase: contiguous row-group range [g0, g1)
 // ------------------------------------------------------------------------------------------
-struct MatSched {
-    int RT, CT, KT, C;
-    int g0, g1;
-    int gs[3];        // row groups per segment
-    bool paired;
-};
-__device__ __forceinline__ MatSched make_sched(const Seg* seg, int nseg, int C, const MatCfg& cfg, bool paired) {
-    MatSched s;
-    s.C = C;
-    s.RT = (kConsumerWarps / cfg.WC) * cfg.RPW;
-    s.CT = cfg.WC * 256 * cfg.CPW;
-    s.KT = (C + s.CT - 1) / s.CT;
-    s.paired = paired;
-    int G = 0;
-    for (int i = 0; i < 3; ++i) {
-        s.gs[i] = (i < nseg) ? (seg[i].rows + s.RT - 1) / s.RT : 0;
-        if (!paired || i == 0) G += s.gs[i];
-    }
-    s.g0 = (int)(((long long)G * blockIdx.x) / gridDim.x);
-    s.g1 = (int)(((long long)G * (blockIdx.x + 1)) / gridDim.x);
-    return s;
+__device__ __forceinline__ void cta_groups(const PhaseDesc& d, int& g0, int& g1) {
+    const unsigned G = (unsigned)d.G, n = gridDim.x, b = blockIdx.x;
+    g0 = (int)((G * b) / n);
+    g1 = (int)((G * (b + 1)) / n);
 }
-__device__ __forceinline__ void locate_group(const MatSched& s, int g, int& segi, int& lg) {
+__device__ __forceinline__ void locate_group(const PhaseDesc& d, int g, int& segi, int& lg) {
     segi = 0; lg = g;
-    if (!s.paired) {
-        while (segi < 2 && lg >= s.gs[segi]) { lg -= s.gs[segi]; ++segi; }
+    if (!d.paired) {
+        while (segi < 2 && lg >= d.gs[segi]) { lg -= d.gs[segi]; ++segi; }
     }
 }
 
@@ -185,41 +190,54 @@ __device__ __forceinline__ void locate_group(const MatSched& s, int g, int& segi
 // ------------------------------------------------------------------------------------------
 struct Ring {
     uint32_t slot_base, full_base, empty_base;
-    uint32_t tc;   // tiles issued / consumed so far
-    __device__ __forceinline__ uint32_t slot() const { return tc % kNumSlots; }
-    __device__ __forceinline__ uint32_t round() const { return tc / kNumSlots; }
-    __device__ __forceinline__ uint32_t slot_addr() const { return slot_base + slot() * kSlotBytes; }
-    __device__ __forceinline__ uint32_t full_bar() const { return full_base + slot() * 8; }
-    __device__ __forceinline__ uint32_t empty_bar() const { return empty_base + slot() * 8; }
+    uint32_t tc;          // tiles issued / consumed so far
+    long long wait_cyc;   // profiling: cycles spent waiting on the ring
+    uint32_t sl, par;     // current slot and its phase parity (kept incrementally: no modulo per tile)
+    __device__ __forceinline__ Ring(uint32_t sb, uint32_t fb, uint32_t eb, uint32_t tc_, long long w)
+        : slot_base(sb), full_base(fb), empty_base(eb), tc(tc_), wait_cyc(w), sl(tc_ % kNumSlots), par((tc_ / kNumSlots) & 1u) {}
+    __device__ __forceinline__ void advance() { ++tc; if (++sl == kNumSlots) { sl = 0; par ^= 1u; } }
+    __device__ __forceinline__ uint32_t slot() const { return sl; }
+    __device__ __forceinline__ uint32_t full_parity() const { return par; }
+    __device__ __forceinline__ uint32_t empty_parity() const { return par ^ 1u; }
+    __device__ __forceinline__ uint32_t slot_addr() const { return slot_base + sl * kSlotBytes; }
+    __device__ __forceinline__ uint32_t full_bar() const { return full_base + sl * 8; }
+    __device__ __forceinline__ uint32_t empty_bar() const { return empty_base + sl * 8; }
 };
 
-__device__ __forceinline__ bool produce_mat_phase(const DecParams& p, Ring& ring, const Seg* seg, int nseg, int C,
-                                                  const MatCfg& cfg, bool paired) {
+__device__ __forceinline__ bool produce_mat_phase(const DecParams& p, Ring& ring, const PhaseDesc& d, const uint16_t* w0p,
+                                               const uint16_t* w1p, const uint16_t* w2p) {
     const int lane = threadIdx.x & 31;
-    const MatSched s = make_sched(seg, nseg, C, cfg, paired);
-    for (int g = s.g0; g < s.g1; ++g) {
+    int g0, g1;
+    cta_groups(d, g0, g1);
+    const int C = d.C;
+    for (int g = g0; g < g1; ++g) {
         int segi, lg;
-        locate_group(s, g, segi, lg);
-        const int nsub = paired ? 2 : 1;
+        locate_group(d, g, segi, lg);
+        const int nsub = d.paired ? 2 : 1;
         for (int sub = 0; sub < nsub; ++sub) {
-            const Seg& sg = seg[paired ? sub : segi];
-            const int row0 = lg * s.RT;
-            const int nrows = min(s.RT, sg.rows - row0);
-            for (int kt = 0; kt < s.KT; ++kt) {
-                const int col0 = kt * s.CT;
-                const int ncols = min(s.CT, C - col0);
-                if (!mbar_wait(p, ring.empty_bar(), (ring.round() & 1u) ^ 1u, 1)) return false;
+            const int si = d.paired ? sub : segi;
+            const int row0 = lg * d.RT;
+            const int nrows = min(d.RT, d.rows[si] - row0);
+            for (int kt = 0; kt < d.KT; ++kt) {
+                const int col0 = kt * d.CT;
+                const int ncols = min(d.CT, C - col0);
+                const long long t0 = p.prof ? clock64() : 0;
+                if (!mbar_wait(p, ring.empty_bar(), ring.empty_parity(), 1)) return false;
+                if (p.prof) ring.wait_cyc += clock64() - t0;
                 const uint32_t dst = ring.slot_addr(), fb = ring.full_bar();
                 if (lane == 0) mbar_expect_tx(fb, (uint32_t)nrows * ncols * 2u);
                 __syncwarp();
-                const uint16_t* src = sg.W + (size_t)row0 * C + col0;
+                const uint16_t* src = (si == 0 ? w0p : si == 1 ? w1p : w2p) + (size_t)row0 * C + col0;
                 if (ncols == C) {
-                    if (lane == 0) bulk_g2s(dst, src, (uint32_t)nrows * ncols * 2u, fb);
+                    // rows are contiguous: split the tile into <= 4 KB pieces issued by different lanes
+                    const uint32_t total = (uint32_t)nrows * ncols * 2u;
+                    for (uint32_t off = (uint32_t)lane * 4096u; off < total; off += 32u * 4096u)
+                        bulk_g2s(dst + off, (const char*)src + off, min(4096u, total - off), fb);
                 } else {
                     for (int r = lane; r < nrows; r += 32)
                         bulk_g2s(dst + (uint32_t)r * ncols * 2u, src + (size_t)r * C, (uint32_t)ncols * 2u, fb);
                 }
-                ++ring.tc;
+                ring.advance();
             }
         }
     }
@@ -255,11 +273,13 @@ __device__ __forceinline__ bool produce_att_phase(const DecParams& p, Ring& ring
             const int np = min(p.att_tpos, pb - pos);
             const uint32_t bytes = (uint32_t)np * D * 4u;
             for (int kv = 0; kv < 2; ++kv) {
-                if (!mbar_wait(p, ring.empty_bar(), (ring.round() & 1u) ^ 1u, 2)) return false;
+                const long long w0 = p.prof ? clock64() : 0;
+                if (!mbar_wait(p, ring.empty_bar(), ring.empty_parity(), 2)) return false;
+                if (p.prof) ring.wait_cyc += clock64() - w0;
                 const float* base = (kv == 0 ? L.key_cache : L.value_cache) + ((size_t)h * p.n_ctx + pos) * D;
                 if (lane == 0) { mbar_expect_tx(ring.full_bar(), bytes); bulk_g2s(ring.slot_addr(), base, bytes, ring.full_bar()); }
                 __syncwarp();
-                ++ring.tc;
+                ring.advance();
             }
         }
     }
@@ -267,24 +287,31 @@ __device__ __forceinline__ bool produce_att_phase(const DecParams& p, Ring& ring
 }
 
 __device__ void producer_main(const DecParams& p, Ring ring) {
-    for (int l = 0; l < p.n_layer; ++l) {
-        const thk_llama_layer L = p.layers[l];
-        { Seg s[3] = {{L.wq, p.Eh}, {L.wk, p.Eh}, {L.wv, p.Eh}};
-          if (!produce_mat_phase(p, ring, s, 3, p.n_embd, p.cfg_qkv, false)) return; }
-        if (!produce_att_phase(p, ring, L)) return;
-        { Seg s[3] = {{L.wo, p.n_embd}, {nullptr, 0}, {nullptr, 0}};
-          if (!produce_mat_phase(p, ring, s, 1, p.Eh, p.cfg_wo, false)) return; }
-        { Seg s[3] = {{L.w1, p.Fh}, {L.w3, p.Fh}, {nullptr, 0}};
-          if (!produce_mat_phase(p, ring, s, 2, p.n_embd, p.cfg_w13, true)) return; }
-        { Seg s[3] = {{L.w2, p.n_embd}, {nullptr, 0}, {nullptr, 0}};
-          if (!produce_mat_phase(p, ring, s, 1, p.Fh, p.cfg_w2, false)) return; }
+    const long long t0 = clock64();
+    const int nsteps = 5 * p.n_layer + 1;
+    int l = 0, k = 0;                                     // same step order as the consumers (StepKind)
+    bool ok = true;
+    for (int i = 0; i < nsteps && ok; ++i) {
+        const thk_llama_layer* L = p.layers + (l < p.n_layer ? l : p.n_layer - 1);
+        if (k == 1) {
+            ok = produce_att_phase(p, ring, *L);
+        } else {
+            const int ph = k == 0 ? PH_QKV : k == 2 ? PH_WO : k == 3 ? PH_W13 : k == 4 ? PH_W2 : PH_OUT;
+            const uint16_t* w0 = k == 0 ? L->wq : k == 2 ? L->wo : k == 3 ? L->w1 : k == 4 ? L->w2 : p.out_w;
+            const uint16_t* w1 = k == 0 ? L->wk : k == 3 ? L->w3 : nullptr;
+            const uint16_t* w2 = k == 0 ? L->wv : nullptr;
+            ok = produce_mat_phase(p, ring, p.ph[ph], w0, w1, w2);
+        }
+        if (k == 4) { ++l; k = (l < p.n_layer) ? 0 : 5; } else ++k;
     }
-    Seg s[3] = {{p.out_w, p.Vl}, {nullptr, 0}, {nullptr, 0}};
-    produce_mat_phase(p, ring, s, 1, p.n_embd, p.cfg_out, false);
+    if (p.prof && (threadIdx.x & 31) == 0) {
+        unsigned long long* stt = p.prof + (size_t)gridDim.x * kProfPhases * 8 + (size_t)blockIdx.x * 4;
+        stt[0] = (unsigned long long)ring.wait_cyc; stt[1] = (unsigned long long)(clock64() - t0); stt[2] = ring.tc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
-// CONSUMERS
+// CONSUMERS: warps 1..8 do the math, warp 9 runs the epilogues
 // ------------------------------------------------------------------------------------------
 struct Cons {
     const DecParams& p;
@@ -292,18 +319,24 @@ struct Cons {
     unsigned char* slots;
     float* xs;
     SmemMisc* sm;
-    int ct, cw, lane;        // consumer thread id 0..255, consumer warp 0..7, lane
+    int ct, cw, lane;        // math thread id 0..255 (epilogue warp: 256..287), math warp 0..7, lane
     unsigned nbar;           // grid barriers passed
     bool ok;
-    int redbuf;
 };
 
+__device__ __forceinline__ void prof_mark(const Cons& c, int slot) {
+    if (c.p.prof && c.ct == 0 && c.nbar < (unsigned)kProfPhases)
+        c.p.prof[((size_t)blockIdx.x * kProfPhases + c.nbar) * 8 + slot] = gtimer();
+}
+
+// Grid-wide barrier between data-dependent phases.  Every math and epilogue thread has issued its
+// global writes; bar.sync orders them before thread 0's gpu-scope release (cumulativity), and the
+// acquire + second bar.sync make the other CTAs' writes visible to all threads here (read with .cg).
 __device__ __forceinline__ void grid_barrier(Cons& c) {
-    // all consumer threads have issued their global writes for this phase
-    __threadfence();
-    consumer_bar();
+    prof_mark(c, PROF_ARRIVE);
+    bar_sync(BAR_ALL, kMathThreads + 32);
+    ++c.nbar;
     if (c.ct == 0) {
-        ++c.nbar;
         red_release_add(c.p.bar_ctr, 1u);
         const unsigned target = c.nbar * gridDim.x;
         if (ld_acquire_u32(c.p.bar_ctr) < target) {
@@ -316,73 +349,120 @@ __device__ __forceinline__ void grid_barrier(Cons& c) {
                 }
             }
         }
-    } else {
-        ++c.nbar;
     }
-    consumer_bar();
+    bar_sync(BAR_ALL, kMathThreads + 32);
+    prof_mark(c, PROF_START);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* base, int bytes, int tid, int nthreads) {
+    for (int off = tid * 128; off < bytes; off += nthreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)base + off));
 }
 
 // xs <- rmsnorm(src) * gain   (cmdbuf_rms_norm + cmdbuf_row_element_multiply, th.cpp:1153-1200,1298-1315)
 __device__ __forceinline__ void prologue_norm(Cons& c, const float* src, const float* gain, int n) {
+    constexpr int kHold = 4;                         // float4s kept in registers per thread (n <= 4096)
+    float4 v[kHold], g[kHold];
     float ss = 0.f;
-    for (int i = c.ct * 4; i < n; i += kConsumerThreads * 4) {
-        const float4 v = __ldcg((const float4*)(src + i));
-        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    const bool held = n <= kHold * kMathThreads * 4;
+    if (held) {
+#pragma unroll
+        for (int k = 0; k < kHold; ++k) {
+            const int i = (c.ct + k * kMathThreads) * 4;
+            if (i < n) { v[k] = __ldcg((const float4*)(src + i)); g[k] = __ldg((const float4*)(gain + i)); }
+        }
+#pragma unroll
+        for (int k = 0; k < kHold; ++k) {
+            const int i = (c.ct + k * kMathThreads) * 4;
+            if (i < n) { ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss); ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss); }
+        }
+    } else {
+        for (int i = c.ct * 4; i < n; i += kMathThreads * 4) {
+            const float4 t = __ldcg((const float4*)(src + i));
+            ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
+        }
     }
     ss = warp_sum(ss);
     if (c.lane == 0) c.sm->norm_part[c.cw] = ss;
-    consumer_bar();
+    bar_sync(BAR_MATH, kMathThreads);
     float tot = 0.f;
 #pragma unroll
-    for (int w = 0; w < kConsumerWarps; ++w) tot += c.sm->norm_part[w];
+    for (int w = 0; w < kMathWarps; ++w) tot += c.sm->norm_part[w];
     const float inv = 1.0f / sqrtf(tot / (float)n + 1e-6f);
-    for (int i = c.ct * 4; i < n; i += kConsumerThreads * 4) {
-        const float4 v = __ldcg((const float4*)(src + i));
-        const float4 g = __ldg((const float4*)(gain + i));
-        float4 o;
-        o.x = (v.x * inv) * g.x; o.y = (v.y * inv) * g.y; o.z = (v.z * inv) * g.z; o.w = (v.w * inv) * g.w;
-        *(float4*)(c.xs + xs_index(i)) = o;
+    if (held) {
+#pragma unroll
+        for (int k = 0; k < kHold; ++k) {
+            const int i = (c.ct + k * kMathThreads) * 4;
+            if (i < n) {
+                float4 o;
+                o.x = (v[k].x * inv) * g[k].x; o.y = (v[k].y * inv) * g[k].y; o.z = (v[k].z * inv) * g[k].z; o.w = (v[k].w * inv) * g[k].w;
+                *(float4*)(c.xs + xs_index(i)) = o;
+            }
+        }
+    } else {
+        for (int i = c.ct * 4; i < n; i += kMathThreads * 4) {
+            const float4 t = __ldcg((const float4*)(src + i));
+            const float4 gg = __ldg((const float4*)(gain + i));
+            float4 o;
+            o.x = (t.x * inv) * gg.x; o.y = (t.y * inv) * gg.y; o.z = (t.z * inv) * gg.z; o.w = (t.w * inv) * gg.w;
+            *(float4*)(c.xs + xs_index(i)) = o;
+        }
     }
-    consumer_bar();
+    bar_sync(BAR_MATH, kMathThreads);
+    prof_mark(c, PROF_PROLOGUE);
 }
 __device__ __forceinline__ void prologue_copy(Cons& c, const float* src, int n) {
-    for (int i = c.ct * 4; i < n; i += kConsumerThreads * 4)
+    for (int i = c.ct * 4; i < n; i += kMathThreads * 4)
         *(float4*)(c.xs + xs_index(i)) = __ldcg((const float4*)(src + i));
-    consumer_bar();
+    bar_sync(BAR_MATH, kMathThreads);
+    prof_mark(c, PROF_PROLOGUE);
 }
 
-// one tile: acc[r] += sum over this warp's columns of W[row][col] * x[col]
+// 8 weights (one uint4 of f16) times 8 activations into two independent accumulators
+__device__ __forceinline__ void fma8(const uint4& w, const float4& x0, const float4& x1, float& a0, float& a1) {
+    float2 f;
+    f = h2_to_f2(w.x); a0 = fmaf(x0.x, f.x, a0); a1 = fmaf(x0.y, f.y, a1);
+    f = h2_to_f2(w.y); a0 = fmaf(x0.z, f.x, a0); a1 = fmaf(x0.w, f.y, a1);
+    f = h2_to_f2(w.z); a0 = fmaf(x1.x, f.x, a0); a1 = fmaf(x1.y, f.y, a1);
+    f = h2_to_f2(w.w); a0 = fmaf(x1.z, f.x, a0); a1 = fmaf(x1.w, f.y, a1);
+}
+
+// One tile: acc[r][0..1] += sum over this warp's columns of W[row][col] * x[col].  Per 256-column
+// chunk all shared-memory loads are issued before the FMAs; branches are warp-uniform except in the
+// last partial chunk of a shard.
 template <int RPW, int CPW>
 __device__ __forceinline__ void tile_fma(const unsigned char* slot, const float* xs, int WC, int wr, int wc, int lane,
-                                         int col0, int nrows, int ncols, float (&acc)[8]) {
+                                         int col0, int nrows, int ncols, float (&acc)[kRC][2]) {
+    const int row_base = wr * RPW;
+    const bool full_rows = row_base + RPW <= nrows;
 #pragma unroll
     for (int cp = 0; cp < CPW; ++cp) {
-        const int col = ((cp * WC + wc) << 8) + (lane << 3);
-        if (col < ncols) {
-            const float* xp = xs + (col0 + ((cp * WC + wc) << 8)) + (lane << 2);
+        const int cbase = (cp * WC + wc) << 8;                 // first column of this warp's chunk in the tile
+        if (cbase >= ncols) break;                             // warp-uniform
+        const int col = cbase + (lane << 3);
+        const float* xp = xs + col0 + cbase + (lane << 2);
+        const unsigned char* wp = slot + ((size_t)row_base * ncols + col) * 2;
+        if (cbase + 256 <= ncols && full_rows) {               // warp-uniform fast path
+            const float4 x0 = *(const float4*)xp;
+            const float4 x1 = *(const float4*)(xp + 128);
+            uint4 w[RPW];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) w[r] = *(const uint4*)(wp + (size_t)r * ncols * 2);
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) fma8(w[r], x0, x1, acc[r][0], acc[r][1]);
+        } else if (col < ncols) {
             const float4 x0 = *(const float4*)xp;
             const float4 x1 = *(const float4*)(xp + 128);
 #pragma unroll
-            for (int r = 0; r < RPW; ++r) {
-                const int row = wr * RPW + r;
-                if (row < nrows) {
-                    const uint4 w = *(const uint4*)(slot + ((size_t)row * ncols + col) * 2);
-                    float2 f;
-                    float a = acc[r];
-                    f = h2_to_f2(w.x); a = fmaf(x0.x, f.x, a); a = fmaf(x0.y, f.y, a);
-                    f = h2_to_f2(w.y); a = fmaf(x0.z, f.x, a); a = fmaf(x0.w, f.y, a);
-                    f = h2_to_f2(w.z); a = fmaf(x1.x, f.x, a); a = fmaf(x1.y, f.y, a);
-                    f = h2_to_f2(w.w); a = fmaf(x1.z, f.x, a); a = fmaf(x1.w, f.y, a);
-                    acc[r] = a;
-                }
-            }
+            for (int r = 0; r < RPW; ++r)
+                if (row_base + r < nrows) fma8(*(const uint4*)(wp + (size_t)r * ncols * 2), x0, x1, acc[r][0], acc[r][1]);
         }
     }
 }
 
 // transposing warp reduction of RPW accumulators: afterwards lane (row << (5-log2 RPW)) holds row's sum
 template <int RPW>
-__device__ __forceinline__ float reduce_rows(float (&v)[8], int lane) {
+__device__ __forceinline__ float reduce_rows(float (&v)[kRC], int lane) {
     int off = 16;
 #pragma unroll
     for (int n = RPW; n > 1; n >>= 1) {
@@ -401,85 +481,113 @@ __device__ __forceinline__ float reduce_rows(float (&v)[8], int lane) {
     return r;
 }
 
-enum EpiKind { EPI_QKV, EPI_WO, EPI_W13, EPI_W2, EPI_OUT };
-
-struct EpiState {
-    float gate;       // W1 result held between the paired sub-groups
-    float best;       // running argmax
-    int best_idx;
-};
-
-__device__ __forceinline__ void rope_pair(float& a, float& b, int i_even, int head_dim, int n_past) {
-    // cmdbuf_RoPE, th.cpp:1457-1492
-    const float theta = powf(10000.0f, (-(float)i_even) / (float)head_dim);
-    float s, c;
-    sincosf((float)n_past * theta, &s, &c);
-    const float x0 = a, x1 = b;
-    a = x0 * c - x1 * s;
-    b = x0 * s + x1 * c;
-}
-
+// ---- math warps: stream tiles, leave per-warp partial row sums in sm->red[buf] for the epilogue warp ----
 template <int RPW, int CPW>
-__device__ __forceinline__ void consume_mat_phase_t(Cons& c, const Seg* seg, int nseg, int C, const MatCfg& cfg, bool paired,
-                                                    EpiKind kind, const thk_llama_layer* L, EpiState& es) {
+__device__ __forceinline__ void math_mat_phase_t(Cons& c, const PhaseDesc& d) {
     const DecParams& p = c.p;
-    const MatSched s = make_sched(seg, nseg, C, cfg, paired);
-    const int WC = cfg.WC;
+    int g0, g1;
+    cta_groups(d, g0, g1);
+    const int WC = d.WC, C = d.C;
     const int wr = c.cw / WC, wc = c.cw % WC;
-    constexpr int kLog = (RPW == 8) ? 3 : (RPW == 4) ? 2 : 1;
-    for (int g = s.g0; g < s.g1; ++g) {
+    constexpr int kLog = (RPW == 8) ? 3 : (RPW == 4) ? 2 : (RPW == 2) ? 1 : 0;
+    unsigned gq = 0;                                            // (group, sub) pairs handed to the epilogue warp
+    for (int g = g0; g < g1; ++g) {
         int segi, lg;
-        locate_group(s, g, segi, lg);
-        const int nsub = paired ? 2 : 1;
+        locate_group(d, g, segi, lg);
+        const int nsub = d.paired ? 2 : 1;
         for (int sub = 0; sub < nsub; ++sub) {
-            const int si = paired ? sub : segi;
-            const int row0 = lg * s.RT;
-            const int nrows = min(s.RT, seg[si].rows - row0);
-            float acc[8];
+            const int si = d.paired ? sub : segi;
+            const int row0 = lg * d.RT;
+            const int nrows = min(d.RT, d.rows[si] - row0);
+            float acc[kRC][2];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-            for (int kt = 0; kt < s.KT; ++kt) {
-                const int col0 = kt * s.CT;
-                const int ncols = min(s.CT, C - col0);
-                if (c.ok) c.ok = mbar_wait(p, c.ring.full_bar(), c.ring.round() & 1u, 3);
+            for (int r = 0; r < kRC; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+            for (int kt = 0; kt < d.KT; ++kt) {
+                const int col0 = kt * d.CT;
+                const int ncols = min(d.CT, C - col0);
+                const long long w0 = p.prof ? clock64() : 0;
+                if (c.ok) c.ok = mbar_wait(p, c.ring.full_bar(), c.ring.full_parity(), 3);
+                if (p.prof) c.ring.wait_cyc += clock64() - w0;
+                if (g == g0 && sub == 0 && kt == 0) prof_mark(c, PROF_FIRST_TILE);
                 if (c.ok) tile_fma<RPW, CPW>(c.slots + (size_t)c.ring.slot() * kSlotBytes, c.xs, WC, wr, wc, c.lane, col0, nrows, ncols, acc);
                 __syncwarp();
                 if (c.lane == 0) mbar_arrive(c.ring.empty_bar());
-                ++c.ring.tc;
+                c.ring.advance();
             }
-            const float rsum = reduce_rows<RPW>(acc, c.lane);
-            const int rb = c.redbuf;
-            if ((c.lane & ((32 >> kLog) - 1)) == 0) c.sm->red[rb][wc][wr * RPW + (c.lane >> (5 - kLog))] = rsum;
-            consumer_bar();
-            c.redbuf ^= 1;
-            // ---- epilogue: thread t owns row row0 + t of this group ----
-            const int t = c.ct;
-            if (t < nrows) {
+            float v[kRC];
+#pragma unroll
+            for (int r = 0; r < kRC; ++r) v[r] = acc[r][0] + acc[r][1];
+            const float rsum = reduce_rows<RPW>(v, c.lane);
+            const int buf = gq & 1;
+            if (gq >= 2) bar_sync(BAR_B0 + buf, kMathThreads + 32);      // epilogue warp is done with this buffer
+            if ((c.lane & ((32 >> kLog) - 1)) == 0) c.sm->red[buf][wc][wr * RPW + (c.lane >> (5 - kLog))] = rsum;
+            bar_arrive(BAR_A0 + buf, kMathThreads + 32);                 // partials ready (non-blocking)
+            ++gq;
+        }
+    }
+    for (unsigned k = gq >= 2 ? gq - 2 : 0; k < gq; ++k) bar_sync(BAR_B0 + (k & 1), kMathThreads + 32);   // drain
+    prof_mark(c, PROF_LAST_TILE);
+    if (p.prof && c.ct == 0 && c.nbar < (unsigned)kProfPhases) {
+        p.prof[((size_t)blockIdx.x * kProfPhases + c.nbar) * 8 + PROF_WAIT_FULL] = (unsigned long long)c.ring.wait_cyc;
+        c.ring.wait_cyc = 0;
+    }
+}
+
+// ---- epilogue warp ----
+enum EpiKind { EPI_QKV, EPI_WO, EPI_W13, EPI_W2, EPI_OUT };
+struct EpiState { float gate[2]; float best; int best_idx; };
+
+__device__ __forceinline__ void epi_mat_phase(Cons& c, const PhaseDesc& d, EpiKind kind, const thk_llama_layer* L, EpiState& es) {
+    const DecParams& p = c.p;
+    int g0, g1;
+    cta_groups(d, g0, g1);
+    const int WC = d.WC, D = p.head_dim;
+    unsigned gq = 0;
+    for (int g = g0; g < g1; ++g) {
+        int segi, lg;
+        locate_group(d, g, segi, lg);
+        const int nsub = d.paired ? 2 : 1;
+        for (int sub = 0; sub < nsub; ++sub) {
+            const int si = d.paired ? sub : segi;
+            const int row0 = lg * d.RT;
+            const int nrows = min(d.RT, d.rows[si] - row0);
+            float resid[2] = {0.f, 0.f};
+            if (kind == EPI_WO || kind == EPI_W2) {               // residual operand: load before waiting for the sums
+                const float* rs = (kind == EPI_WO) ? p.x : p.h1;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) { const int t = c.lane + 32 * k; if (t < nrows) resid[k] = __ldcg(rs + row0 + t); }
+            }
+            const int buf = gq & 1;
+            bar_sync(BAR_A0 + buf, kMathThreads + 32);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int t = c.lane + 32 * k;
+                if (t >= nrows) continue;
                 float y = 0.f;
-                for (int w = 0; w < WC; ++w) y += c.sm->red[rb][w][t];
+                for (int w = 0; w < WC; ++w) y += c.sm->red[buf][w][t];
                 const int r = row0 + t;
                 switch (kind) {
-                case EPI_QKV: {
-                    const int D = p.head_dim;
+                case EPI_QKV:
                     if (si == 2) {                                   // V: append (th-llama.cpp:338)
                         L->value_cache[((size_t)(r / D) * p.n_ctx + p.n_past) * D + (r % D)] = y;
-                    } else if ((t & 1) == 0) {                       // Q / K: rotate the pair (t, t+1)
+                    } else if ((t & 1) == 0) {                       // Q / K: rotate the pair (t, t+1), th.cpp:1457-1492
                         float y1 = 0.f;
-                        for (int w = 0; w < WC; ++w) y1 += c.sm->red[rb][w][t + 1];
-                        rope_pair(y, y1, r % D, D, p.n_past);
-                        if (si == 0) { p.q[r] = y; p.q[r + 1] = y1; }
+                        for (int w = 0; w < WC; ++w) y1 += c.sm->red[buf][w][t + 1];
+                        const float2 cs = c.sm->rope[(r % D) >> 1];
+                        const float a = y * cs.x - y1 * cs.y, b = y * cs.y + y1 * cs.x;
+                        if (si == 0) { p.q[r] = a; p.q[r + 1] = b; }
                         else {
                             float* kc = L->key_cache + ((size_t)(r / D) * p.n_ctx + p.n_past) * D + (r % D);
-                            kc[0] = y; kc[1] = y1;                  // th-llama.cpp:337
+                            kc[0] = a; kc[1] = b;                    // th-llama.cpp:337
                         }
                     }
-                } break;
-                case EPI_WO: p.h1[r] = __ldcg(p.x + r) + y; break;                    // th-llama.cpp:409
-                case EPI_W13:
-                    if (sub == 0) es.gate = y;
-                    else { const float gv = es.gate; p.ff[r] = (gv / (1.0f + expf(-gv))) * y; }   // :436,:438
                     break;
-                case EPI_W2: p.x[r] = __ldcg(p.h1 + r) + y; break;                    // th-llama.cpp:447
+                case EPI_WO: p.h1[r] = resid[k] + y; break;                            // th-llama.cpp:409
+                case EPI_W13:
+                    if (sub == 0) es.gate[k] = y;
+                    else { const float gv = es.gate[k]; p.ff[r] = (gv / (1.0f + expf(-gv))) * y; }   // :436,:438
+                    break;
+                case EPI_W2: p.x[r] = resid[k] + y; break;                             // th-llama.cpp:447
                 case EPI_OUT: {
                     if (p.logits) p.logits[r] = y;
                     const int gid = p.tp_rank * p.Vl + r;
@@ -487,19 +595,15 @@ __device__ __forceinline__ void consume_mat_phase_t(Cons& c, const Seg* seg, int
                 } break;
                 }
             }
+            __syncwarp();
+            bar_arrive(BAR_B0 + buf, kMathThreads + 32);
+            ++gq;
         }
     }
 }
 
-__device__ __forceinline__ void consume_mat_phase(Cons& c, const Seg* seg, int nseg, int C, const MatCfg& cfg, bool paired,
-                                                  EpiKind kind, const thk_llama_layer* L, EpiState& es) {
-    if (cfg.RPW == 8) consume_mat_phase_t<8, 1>(c, seg, nseg, C, cfg, paired, kind, L, es);
-    else if (cfg.RPW == 4) consume_mat_phase_t<4, 2>(c, seg, nseg, C, cfg, paired, kind, L, es);
-    else consume_mat_phase_t<2, 4>(c, seg, nseg, C, cfg, paired, kind, L, es);
-}
-
 // ------------------------------------------------------------------------------------------
-// attention: single query, split-KV, online softmax
+// attention: single query, split-KV, online softmax (math warps only)
 // (cmdbuf_mat_mul QK^T * 1/sqrt(D), cmdbuf_row_softmax, cmdbuf_mat_mul P*V; th-llama.cpp:365-380)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -508,12 +612,19 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return s;
 }
 
-__device__ void consume_att_phase(Cons& c, const thk_llama_layer& L) {
+__device__ __forceinline__ void math_att_phase(Cons& c, const thk_llama_layer& L) {
     const DecParams& p = c.p;
     const AttSched a = make_att(p);
     const int D = p.head_dim, nvec = D >> 2;
     const float scale = 1.0f / sqrtf((float)D);
     const bool act = c.lane < nvec;
+    // K scoring: 4 threads per position, each owns a quarter of the head dimension (needs D % 16 == 0)
+    const bool quad = (D % 16 == 0) && D <= 128;
+    const int kq = c.ct & 3, kp = c.ct >> 2, nv = D >> 4;       // quarter, position slot 0..63, float4s per quarter
+    int rot = 0;                                                // bank-conflict-free visiting order of the quarter's float4s
+    if (nv == 8) rot = (kq + 4 * (kp & 1)) & 7;
+    else if (nv == 4) rot = ((kq >> 1) + 2 * (kp & 1)) & 3;
+    else if (nv == 2) rot = kp & 1;
     for (int u = blockIdx.x; u < p.Hl * a.S; u += gridDim.x) {
         const int h = u / a.S, sp = u % a.S;
         const int pa = (int)(((long long)a.N * sp) / a.S);
@@ -522,26 +633,48 @@ __device__ void consume_att_phase(Cons& c, const thk_llama_layer& L) {
         const bool has_new = (pb_full == a.N);
         float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) q4 = __ldcg((const float4*)(p.q + h * D) + c.lane);
+        float4 qr[8];
+        if (quad) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nv) qr[j] = __ldcg((const float4*)(p.q + h * D + kq * (D >> 2)) + ((j + rot) & (nv - 1)));
+        }
         float m = -INFINITY, lsum = 0.f;
         float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
         int buf = 0;
         for (int pos = pa; pos < pb; pos += p.att_tpos) {
             const int np = min(p.att_tpos, pb - pos);
             // K tile -> scores
-            if (c.ok) c.ok = mbar_wait(p, c.ring.full_bar(), c.ring.round() & 1u, 4);
+            if (c.ok) c.ok = mbar_wait(p, c.ring.full_bar(), c.ring.full_parity(), 4);
             if (c.ok) {
                 const float* kt = (const float*)(c.slots + (size_t)c.ring.slot() * kSlotBytes);
-                for (int j = c.cw; j < np; j += kConsumerWarps) {
-                    float sdot = 0.f;
-                    if (act) sdot = dot4(q4, *(const float4*)(kt + j * D + c.lane * 4));
-                    sdot = warp_sum(sdot) * scale;
-                    if (c.lane == 0) c.sm->sc[buf][j] = sdot;
+                if (quad) {
+                    for (int j0 = 0; j0 < np; j0 += kMathThreads / 4) {
+                        const int j = j0 + kp;
+                        float sdot = 0.f;
+                        if (j < np) {
+                            const float4* kr = (const float4*)(kt + (size_t)j * D + kq * (D >> 2));
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (i < nv) sdot += dot4(qr[i], kr[(i + rot) & (nv - 1)]);
+                        }
+                        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+                        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+                        if (kq == 0 && j < np) c.sm->sc[buf][j] = sdot * scale;
+                    }
+                } else {
+                    for (int j = c.cw; j < np; j += kMathWarps) {
+                        float sdot = 0.f;
+                        if (act) sdot = dot4(q4, *(const float4*)(kt + j * D + c.lane * 4));
+                        sdot = warp_sum(sdot) * scale;
+                        if (c.lane == 0) c.sm->sc[buf][j] = sdot;
+                    }
                 }
             }
             __syncwarp();
             if (c.lane == 0) mbar_arrive(c.ring.empty_bar());
-            ++c.ring.tc;
-            consumer_bar();
+            c.ring.advance();
+            bar_sync(BAR_MATH, kMathThreads);
             float bmax = -INFINITY;
             for (int j = c.lane; j < np; j += 32) bmax = fmaxf(bmax, c.sm->sc[buf][j]);
             bmax = warp_max(bmax);
@@ -550,10 +683,10 @@ __device__ void consume_att_phase(Cons& c, const thk_llama_layer& L) {
             lsum *= corr; o4.x *= corr; o4.y *= corr; o4.z *= corr; o4.w *= corr;
             m = m_new;
             // V tile -> weighted sum
-            if (c.ok) c.ok = mbar_wait(p, c.ring.full_bar(), c.ring.round() & 1u, 5);
+            if (c.ok) c.ok = mbar_wait(p, c.ring.full_bar(), c.ring.full_parity(), 5);
             if (c.ok) {
                 const float* vt = (const float*)(c.slots + (size_t)c.ring.slot() * kSlotBytes);
-                for (int j = c.cw; j < np; j += kConsumerWarps) {
+                for (int j = c.cw; j < np; j += kMathWarps) {
                     const float pj = expf(c.sm->sc[buf][j] - m);
                     lsum += pj;
                     if (act) {
@@ -565,7 +698,7 @@ __device__ void consume_att_phase(Cons& c, const thk_llama_layer& L) {
             }
             __syncwarp();
             if (c.lane == 0) mbar_arrive(c.ring.empty_bar());
-            ++c.ring.tc;
+            c.ring.advance();
             buf ^= 1;
         }
         if (has_new) {   // the token's own K/V row, written by the QKV epilogue of this launch
@@ -591,31 +724,30 @@ __device__ void consume_att_phase(Cons& c, const thk_llama_layer& L) {
         // combine the 8 warps' partial sums (same running max in every warp)
         if (act) *(float4*)(&c.sm->redo[c.cw][c.lane * 4]) = o4;
         if (c.lane == 0) c.sm->redl[c.cw] = lsum;
-        consumer_bar();
+        bar_sync(BAR_MATH, kMathThreads);
         float* part = p.part + (size_t)(h * p.att_max_split + sp) * (D + 2);
         if (c.ct < D) {
             float od = 0.f;
 #pragma unroll
-            for (int w = 0; w < kConsumerWarps; ++w) od += c.sm->redo[w][c.ct];
+            for (int w = 0; w < kMathWarps; ++w) od += c.sm->redo[w][c.ct];
             part[2 + c.ct] = od;
         }
         if (c.ct == 0) {
             float lt = 0.f;
 #pragma unroll
-            for (int w = 0; w < kConsumerWarps; ++w) lt += c.sm->redl[w];
+            for (int w = 0; w < kMathWarps; ++w) lt += c.sm->redl[w];
             part[0] = m; part[1] = lt;
         }
         // last split to finish combines the head (deterministic: fixed split order)
-        __threadfence();
-        consumer_bar();
+        bar_sync(BAR_MATH, kMathThreads);
         if (c.ct == 0) {
+            __threadfence();
             const unsigned prev = atomicAdd(p.head_ctr + h, 1u);
             c.sm->flag = (prev == (unsigned)(a.S - 1));
-            if (c.sm->flag) p.head_ctr[h] = 0u;
+            if (c.sm->flag) { p.head_ctr[h] = 0u; __threadfence(); }
         }
-        consumer_bar();
+        bar_sync(BAR_MATH, kMathThreads);
         if (c.sm->flag) {
-            __threadfence();
             if (c.ct < D) {
                 const float* ph = p.part + (size_t)h * p.att_max_split * (D + 2);
                 float M = -INFINITY;
@@ -630,76 +762,149 @@ __device__ void consume_att_phase(Cons& c, const thk_llama_layer& L) {
                 p.o[h * D + c.ct] = od / Lt;
             }
         }
-        consumer_bar();   // sm->flag / redo reuse
+        bar_sync(BAR_MATH, kMathThreads);   // sm->flag / redo reuse
     }
 }
 
-__device__ void consumer_main(const DecParams& p, Ring ring, unsigned char* slots, float* xs, SmemMisc* sm) {
-    Cons c{p, ring, slots, xs, sm, (int)threadIdx.x - 32, ((int)threadIdx.x - 32) >> 5, (int)threadIdx.x & 31, 0u, true, 0};
-    EpiState es{0.f, 0.f, -1};
+// ---- out-of-line phase bodies ----
+// One out-of-line copy of each phase routine keeps the kernel's instruction footprint small (the
+// fully inlined kernel was 400 KB of SASS and missed the instruction cache at every phase change).
+// State crosses the call boundary BY VALUE (registers), never through a reference to a stack object.
+enum StepKind { K_QKV = 0, K_ATT = 1, K_WO = 2, K_W13 = 3, K_W2 = 4, K_OUT = 5 };
+__device__ __forceinline__ int phase_of(int k) { return k == K_QKV ? PH_QKV : k == K_WO ? PH_WO : k == K_W13 ? PH_W13 : k == K_W2 ? PH_W2 : PH_OUT; }
 
-    // phase E: x <- f32(tok_embeddings[token]) (th-llama.cpp:577-585; device-side like :552-575)
+struct Shared { unsigned char* slots; float* xs; SmemMisc* sm; };
+struct MState { uint32_t tc; int ok; unsigned nbar; long long wait_cyc; };
+struct EpiRet { MState st; EpiState es; };
+
+__device__ __forceinline__ Cons cons_from(const DecParams& p, const Shared& S, const MState& st, bool epi) {
+    Ring ring(smem_u32(S.slots), smem_u32(&S.sm->full[0]), smem_u32(&S.sm->empty[0]), st.tc, st.wait_cyc);
+    const int lane = (int)threadIdx.x & 31;
+    if (epi) return Cons{p, ring, S.slots, S.xs, S.sm, kMathThreads + lane, kMathWarps, lane, st.nbar, st.ok != 0};
+    return Cons{p, ring, S.slots, S.xs, S.sm, (int)threadIdx.x - kMathBase, ((int)threadIdx.x - kMathBase) >> 5, lane, st.nbar, st.ok != 0};
+}
+__device__ __forceinline__ MState state_of(const Cons& c) { return MState{c.ring.tc, c.ok ? 1 : 0, c.nbar, c.ring.wait_cyc}; }
+
+__device__ __noinline__ MState nl_grid_barrier(const DecParams& p, Shared S, MState st, int epi) {
+    Cons c = cons_from(p, S, st, epi != 0);
+    grid_barrier(c);
+    return state_of(c);
+}
+__device__ __noinline__ MState nl_prologue_norm(const DecParams& p, Shared S, MState st, const float* src, const float* gain, int n) {
+    Cons c = cons_from(p, S, st, false);
+    prologue_norm(c, src, gain, n);
+    return state_of(c);
+}
+__device__ __noinline__ MState nl_prologue_copy(const DecParams& p, Shared S, MState st, const float* src, int n) {
+    Cons c = cons_from(p, S, st, false);
+    prologue_copy(c, src, n);
+    return state_of(c);
+}
+template <int RPW, int CPW>
+__device__ __noinline__ MState nl_math_mat(const DecParams& p, Shared S, MState st, int ph) {
+    Cons c = cons_from(p, S, st, false);
+    math_mat_phase_t<RPW, CPW>(c, p.ph[ph]);
+    return state_of(c);
+}
+__device__ __forceinline__ MState math_mat(const DecParams& p, Shared S, MState st, int ph) {
+    const int cpw = p.ph[ph].CPW;
+    if (cpw == 1) return nl_math_mat<kRC, 1>(p, S, st, ph);
+    if (cpw == 2) return nl_math_mat<kRC / 2, 2>(p, S, st, ph);
+    return nl_math_mat<kRC / 4, 4>(p, S, st, ph);
+}
+__device__ __noinline__ MState nl_math_att(const DecParams& p, Shared S, MState st, int layer) {
+    Cons c = cons_from(p, S, st, false);
+    math_att_phase(c, p.layers[layer]);
+    return state_of(c);
+}
+__device__ __noinline__ EpiRet nl_epi_mat(const DecParams& p, Shared S, MState st, EpiState es, int ph, int kind, int layer) {
+    Cons c = cons_from(p, S, st, true);
+    epi_mat_phase(c, p.ph[ph], (EpiKind)kind, layer >= 0 ? p.layers + layer : nullptr, es);
+    return EpiRet{state_of(c), es};
+}
+
+__device__ void math_main(const DecParams& p, Shared S) {
+    MState st{0u, 1, 0u, 0};
+    const int tid = (int)threadIdx.x - kMathBase;
     {
+        Cons c = cons_from(p, S, st, false);
+        prof_mark(c, PROF_START);
+        // phase E: x <- f32(tok_embeddings[token]) (th-llama.cpp:577-585; device-side like :552-575)
         int tok = *p.token;
         if (tok < 0 || tok >= p.n_vocab) { if (c.ct == 0) raise_abort(p, 0x300u, (unsigned)tok, 0); tok = 0; }
         const uint16_t* row = p.emb + (size_t)tok * p.n_embd;
-        for (int i = (blockIdx.x * kConsumerThreads + c.ct); i < p.n_embd; i += gridDim.x * kConsumerThreads)
+        for (int i = (blockIdx.x * kMathThreads + c.ct); i < p.n_embd; i += gridDim.x * kMathThreads)
             p.x[i] = __half2float(__ushort_as_half(row[i]));
         if (blockIdx.x == 0 && c.ct == 0) *p.bar_next = 0u;   // arm the next launch's barrier counter
+        prefetch_l2(p.layers[0].attention_norm, p.n_embd * 4, c.ct, kMathThreads);
     }
-    grid_barrier(c);
-
-    for (int l = 0; l < p.n_layer; ++l) {
-        const thk_llama_layer* Lp = p.layers + l;
-        const thk_llama_layer L = *Lp;
-        prologue_norm(c, p.x, L.attention_norm, p.n_embd);
-        { Seg s[3] = {{L.wq, p.Eh}, {L.wk, p.Eh}, {L.wv, p.Eh}};
-          consume_mat_phase(c, s, 3, p.n_embd, p.cfg_qkv, false, EPI_QKV, Lp, es); }
-        grid_barrier(c);
-        consume_att_phase(c, L);
-        grid_barrier(c);
-        prologue_copy(c, p.o, p.Eh);
-        { Seg s[3] = {{L.wo, p.n_embd}, {nullptr, 0}, {nullptr, 0}};
-          consume_mat_phase(c, s, 1, p.Eh, p.cfg_wo, false, EPI_WO, Lp, es); }
-        grid_barrier(c);
-        prologue_norm(c, p.h1, L.ffn_norm, p.n_embd);
-        { Seg s[3] = {{L.w1, p.Fh}, {L.w3, p.Fh}, {nullptr, 0}};
-          consume_mat_phase(c, s, 2, p.n_embd, p.cfg_w13, true, EPI_W13, Lp, es); }
-        grid_barrier(c);
-        prologue_copy(c, p.ff, p.Fh);
-        { Seg s[3] = {{L.w2, p.n_embd}, {nullptr, 0}, {nullptr, 0}};
-          consume_mat_phase(c, s, 1, p.Fh, p.cfg_w2, false, EPI_W2, Lp, es); }
-        grid_barrier(c);
-    }
-    // final: rmsnorm * norm, logits, greedy argmax (th-llama.cpp:240-268, 826-838)
-    prologue_norm(c, p.x, p.norm, p.n_embd);
-    { Seg s[3] = {{p.out_w, p.Vl}, {nullptr, 0}, {nullptr, 0}};
-      consume_mat_phase(c, s, 1, p.n_embd, p.cfg_out, false, EPI_OUT, nullptr, es); }
-    if (p.next_token || p.next_logit) {
-        // CTA-level argmax over the epilogue threads (thread t saw rows row0+t in ascending groups)
-        if (c.ct < kMaxGroupRows) { sm->bval[c.ct] = es.best; sm->bidx[c.ct] = es.best_idx; }
-        consumer_bar();
-        if (c.ct == 0) {
-            float bv = 0.f; int bi = -1;
-            for (int t = 0; t < kMaxGroupRows; ++t) {
-                const int idx = sm->bidx[t];
-                if (idx < 0) continue;
-                const float v = sm->bval[t];
-                if (bi < 0 || v > bv || (v == bv && idx < bi)) { bv = v; bi = idx; }
-            }
-            p.amax_val[blockIdx.x] = bv; p.amax_idx[blockIdx.x] = bi;
+    st = nl_grid_barrier(p, S, st, 0);
+    const int nsteps = 5 * p.n_layer + 1;
+    int l = 0, k = K_QKV;
+    for (int i = 0; i < nsteps; ++i) {
+        const thk_llama_layer* L = p.layers + (l < p.n_layer ? l : p.n_layer - 1);
+        if (k == K_QKV || k == K_W13 || k == K_OUT) {
+            const float* src = (k == K_W13) ? p.h1 : p.x;
+            const float* gain = (k == K_QKV) ? L->attention_norm : (k == K_W13) ? L->ffn_norm : p.norm;
+            st = nl_prologue_norm(p, S, st, src, gain, p.n_embd);
+        } else if (k == K_WO || k == K_W2) {
+            st = nl_prologue_copy(p, S, st, k == K_WO ? p.o : p.ff, k == K_WO ? p.Eh : p.Fh);
         }
-        grid_barrier(c);
-        if (blockIdx.x == 0 && c.ct == 0) {
-            float bv = 0.f; int bi = -1;
+        if (k == K_ATT) st = nl_math_att(p, S, st, l);
+        else st = math_mat(p, S, st, phase_of(k));
+        if (k == K_WO) prefetch_l2(L->ffn_norm, p.n_embd * 4, tid, kMathThreads);
+        if (k == K_W2) prefetch_l2(l + 1 < p.n_layer ? p.layers[l + 1].attention_norm : p.norm, p.n_embd * 4, tid, kMathThreads);
+        if (k != K_OUT || p.next_token || p.next_logit) st = nl_grid_barrier(p, S, st, 0);
+        if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
+    }
+}
+
+__device__ void epi_main(const DecParams& p, Shared S) {
+    MState st{0u, 1, 0u, 0};
+    EpiState es{{0.f, 0.f}, 0.f, -1};
+    const int lane = (int)threadIdx.x & 31;
+    // RoPE table for this token: cos/sin(n_past * 10000^(-2i/D)) (th.cpp:1478-1482), once per CTA
+    for (int i = lane; i < (p.head_dim >> 1); i += 32) {
+        const float theta = powf(10000.0f, (-(float)(2 * i)) / (float)p.head_dim);
+        float sn, cs;
+        sincosf((float)p.n_past * theta, &sn, &cs);
+        S.sm->rope[i] = make_float2(cs, sn);
+    }
+    __syncwarp();
+    st = nl_grid_barrier(p, S, st, 1);
+    const int nsteps = 5 * p.n_layer + 1;
+    int l = 0, k = K_QKV;
+    for (int i = 0; i < nsteps; ++i) {
+        if (k != K_ATT) {
+            const int kind = k == K_QKV ? EPI_QKV : k == K_WO ? EPI_WO : k == K_W13 ? EPI_W13 : k == K_W2 ? EPI_W2 : EPI_OUT;
+            const EpiRet r = nl_epi_mat(p, S, st, es, phase_of(k), kind, k == K_OUT ? -1 : l);
+            st = r.st; es = r.es;
+        }
+        if (k == K_OUT) break;
+        st = nl_grid_barrier(p, S, st, 1);
+        if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
+    }
+    if (p.next_token || p.next_logit) {
+        // greedy argmax (th-llama.cpp:826-838): lowest index wins ties; warp -> CTA -> grid
+        float bv = es.best; int bi = es.best_idx;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { p.amax_val[blockIdx.x] = bv; p.amax_idx[blockIdx.x] = bi; }
+        st = nl_grid_barrier(p, S, st, 1);
+        if (blockIdx.x == 0 && lane == 0) {
+            float gv = 0.f; int gi = -1;
             for (unsigned b = 0; b < gridDim.x; ++b) {
                 const int idx = __ldcg(p.amax_idx + b);
                 if (idx < 0) continue;
                 const float v = __ldcg(p.amax_val + b);
-                if (bi < 0 || v > bv || (v == bv && idx < bi)) { bv = v; bi = idx; }
+                if (gi < 0 || v > gv || (v == gv && idx < gi)) { gv = v; gi = idx; }
             }
-            if (p.next_token) *p.next_token = bi < 0 ? 0 : bi;
-            if (p.next_logit) *p.next_logit = bv;
+            if (p.next_token) *p.next_token = gi < 0 ? 0 : gi;
+            if (p.next_logit) *p.next_logit = gv;
         }
     }
 }
@@ -712,37 +917,53 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNumSlots; ++i) {
             mbar_init(smem_u32(&sm->full[i]), 1);
-            mbar_init(smem_u32(&sm->empty[i]), kConsumerWarps);
+            mbar_init(smem_u32(&sm->empty[i]), kMathWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    Ring ring{smem_u32(slots), smem_u32(&sm->full[0]), smem_u32(&sm->empty[0]), 0u};
+    Ring ring(smem_u32(slots), smem_u32(&sm->full[0]), smem_u32(&sm->empty[0]), 0u, 0);
+    const Shared S{slots, xs, sm};
     if (threadIdx.x < 32) producer_main(p, ring);
-    else consumer_main(p, ring, slots, xs, sm);
+    else if (threadIdx.x < kMathBase + kMathThreads) math_main(p, S);
+    else epi_main(p, S);
 }
 
 size_t decode_smem_bytes(int max_vec) {
     return (size_t)kNumSlots * kSlotBytes + ((sizeof(SmemMisc) + 127) & ~127) + (size_t)((max_vec + 255) & ~255) * sizeof(float);
 }
 
-MatCfg choose_cfg(int rows_total, int C, bool paired_rows_counted_once, int n_cta) {
-    (void)paired_rows_counted_once;
+PhaseDesc make_phase(int nseg, const int* rows, int C, bool paired, int n_cta) {
+    PhaseDesc d{};
+    d.C = C; d.nseg = nseg; d.paired = paired ? 1 : 0;
+    for (int i = 0; i < 3; ++i) d.rows[i] = i < nseg ? rows[i] : 0;
     const int chunks = (C + 255) / 256;
     int WC = 1;
     while (WC * 2 <= chunks && WC < 8) WC *= 2;
-    const int WR = kConsumerWarps / WC;
+    const int WR = kMathWarps / WC;
     int cap = 1;
     while (cap * WC < chunks && cap < 4) cap *= 2;     // chunks per warp needed to span C, pow2, <= 4
-    const int opts[3][2] = {{8, 1}, {4, 2}, {2, 4}};
-    MatCfg best{WC, 8, 1};
+    int rows_total = 0;
+    for (int i = 0; i < nseg; ++i) if (!paired || i == 0) rows_total += rows[i];
+    const int opts[3][2] = {{kRC, 1}, {kRC / 2, 2}, {kRC / 4, 4}};
+    int RPW = kRC, CPW = 1;
     for (int i = 0; i < 3; ++i) {
         if (opts[i][1] > cap) break;
-        best = MatCfg{WC, opts[i][0], opts[i][1]};
-        const int G = (rows_total + WR * opts[i][0] - 1) / (WR * opts[i][0]);
-        if (G >= 16 * n_cta) break;
+        RPW = opts[i][0]; CPW = opts[i][1];
+        const int G = (rows_total + WR * RPW - 1) / (WR * RPW);
+        if (G >= 8 * n_cta) break;
     }
-    return best;
+    d.WC = WC; d.RPW = RPW; d.CPW = CPW;
+    d.RT = WR * RPW;
+    const int per_tile = WC * CPW;
+    d.KT = (chunks + per_tile - 1) / per_tile;
+    d.CT = ((chunks + d.KT - 1) / d.KT) * 256;          // K split evenly over the tiles
+    d.G = 0;
+    for (int i = 0; i < 3; ++i) {
+        d.gs[i] = i < nseg ? (rows[i] + d.RT - 1) / d.RT : 0;
+        if (!paired || i == 0) d.G += d.gs[i];
+    }
+    return d;
 }
 
 }  // namespace
@@ -761,6 +982,7 @@ struct thk_decoder {
     int grid = 0;
     size_t smem = 0;
     int last_launches = 0;
+    unsigned long long* d_prof = nullptr;
 };
 
 static int check_status(thk_decoder* d) {
@@ -800,11 +1022,15 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     p.Eh = dims->n_embd / tp; p.Fh = dims->n_ff / tp; p.Hl = dims->n_head / tp; p.Vl = dims->n_vocab / tp;
     p.emb = tok_embeddings; p.norm = norm; p.out_w = output;
     d->grid = ctx->sm_count;
-    p.cfg_qkv = choose_cfg(3 * p.Eh, p.n_embd, false, d->grid);
-    p.cfg_wo = choose_cfg(p.n_embd, p.Eh, false, d->grid);
-    p.cfg_w13 = choose_cfg(p.Fh, p.n_embd, true, d->grid);
-    p.cfg_w2 = choose_cfg(p.n_embd, p.Fh, false, d->grid);
-    p.cfg_out = choose_cfg(p.Vl, p.n_embd, false, d->grid);
+    { const int r[3] = {p.Eh, p.Eh, p.Eh}; p.ph[PH_QKV] = make_phase(3, r, p.n_embd, false, d->grid); }
+    { const int r[3] = {p.n_embd, 0, 0}; p.ph[PH_WO] = make_phase(1, r, p.Eh, false, d->grid); }
+    { const int r[3] = {p.Fh, p.Fh, 0}; p.ph[PH_W13] = make_phase(2, r, p.n_embd, true, d->grid); }
+    { const int r[3] = {p.n_embd, 0, 0}; p.ph[PH_W2] = make_phase(1, r, p.Fh, false, d->grid); }
+    { const int r[3] = {p.Vl, 0, 0}; p.ph[PH_OUT] = make_phase(1, r, p.n_embd, false, d->grid); }
+    if (getenv("THK_DEBUG"))
+        for (int i = 0; i < 5; ++i)
+            fprintf(stderr, "phase %d: C=%d WC=%d RPW=%d CPW=%d RT=%d CT=%d KT=%d G=%d\n", i, p.ph[i].C, p.ph[i].WC, p.ph[i].RPW, p.ph[i].CPW,
+                    p.ph[i].RT, p.ph[i].CT, p.ph[i].KT, p.ph[i].G);
     p.att_tpos = kSlotBytes / (D * 4);
     if (p.att_tpos > kMaxTilePos) p.att_tpos = kMaxTilePos;
     p.att_max_split = d->grid / p.Hl > 0 ? d->grid / p.Hl : 1;
@@ -843,7 +1069,7 @@ extern "C" int thk_decoder_destroy(thk_decoder* d) {
     if (!d) return THK_OK;
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
-    cudaFree(d->d_layers); cudaFree(d->scratch); cudaFree(d->ctrl); cudaFree(d->d_tok);
+    cudaFree(d->d_layers); cudaFree(d->scratch); cudaFree(d->ctrl); cudaFree(d->d_tok); cudaFree(d->d_prof);
     delete d;
     return THK_OK;
 }
@@ -887,6 +1113,24 @@ extern "C" int thk_decoder_generate(thk_decoder* d, const int32_t* first_token, 
         if (rc) return rc;
     }
     d->last_launches = n_steps;
+    return THK_OK;
+}
+
+// timeline profile: per CTA, per phase (= grid barriers passed so far), 8 u64 slots of %globaltimer ns
+// (ProfSlot), followed by per-CTA producer stats [empty-wait cycles, total cycles, tiles, 0]
+extern "C" int thk_decoder_profile(thk_decoder* d, int enable, unsigned long long* host_out, int n) {
+    THK_CHECK_ARG(d, "thk_decoder_profile: null argument");
+    if (enable && !d->d_prof) {
+        const size_t nprof = (size_t)d->grid * kProfPhases * 8 + (size_t)d->grid * 4;
+        THK_CUDA(cudaMalloc(&d->d_prof, nprof * sizeof(unsigned long long)));
+        THK_CUDA(cudaMemset(d->d_prof, 0, nprof * sizeof(unsigned long long)));
+    }
+    d->p.prof = enable ? d->d_prof : nullptr;
+    if (host_out && n > 0 && d->d_prof) {
+        THK_CUDA(cudaStreamSynchronize(d->ctx->stream));
+        const size_t nprof = (size_t)d->grid * kProfPhases * 8 + (size_t)d->grid * 4;
+        THK_CUDA(cudaMemcpy(host_out, d->d_prof, sizeof(unsigned long long) * ((size_t)n > nprof ? nprof : (size_t)n), cudaMemcpyDeviceToHost));
+    }
     return THK_OK;
 }
 

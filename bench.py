@@ -163,17 +163,19 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
     if world > 1:
-        import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = None
     stream = torch.cuda.current_stream()
     dev = th.Device(local_rank, stream=stream.cuda_stream)
 
-    if world > 1:
-        raise SystemExit("tensor-parallel bench path not wired yet")
-
     n_past = args.ctx - 1
-    model = th.LlamaModel.synthetic(dev, V, E, NMULT, H, args.layers, args.ctx)
+    model = th.LlamaModel.synthetic(dev, V, E, NMULT, H, args.layers, args.ctx, tp_rank=rank, tp_size=world)
+    if world > 1:
+        from token_hawk_b200 import tp as tpmod
+        tpmod.wire_distributed(model, rank, world)      # peers' exchange regions via CUDA IPC
     model.fill_kv(n_past)
     model.set_token(1)
     for _ in range(max(3, args.warmup)):
@@ -183,6 +185,16 @@ def main():
 
     def barrier():
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- value: device-resident token, K launches between events on the launching stream ----
     sampler = ClockSampler(local_rank)
@@ -194,7 +206,7 @@ def main():
         model.step_async(n_past)
     ev1.record(stream)
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop()
     model.check()
     ms_step = ms_total / args.steps
@@ -214,8 +226,8 @@ def main():
         ev1.record(stream)
         barrier()
         wall = (time.perf_counter() - t0) / ke
-        ms_e2e = max(ev0.elapsed_time(ev1) / ke, wall * 1e3)
-        e2e = {"value": 1e3 / ms_e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": V * 4,
+        ms_e2e = max_over_ranks(max(ev0.elapsed_time(ev1) / ke, wall * 1e3))
+        e2e = {"value": 1e3 / ms_e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": V * 4 + (4 * world if world > 1 else 0),
                "ms_per_step": ms_e2e, "steps": ke, "api": "th_eval_gpu (capi_eval): host token id -> logits in pinned host memory -> host greedy"}
 
     if args.phase_profile:
@@ -231,20 +243,21 @@ def main():
         print("PHASES " + json.dumps(analyze_timeline.summarize(marks, prod, args.layers, args.ctx)), file=sys.stderr)
 
     peak, peak_src = load_peaks()
-    bytes_w = args.layers * 2 * (4 * E * E + 3 * E * F) + 2 * V * E + (2 * args.layers + 1) * 4 * E + 2 * E
-    bytes_total = bytes_w + kv_bytes(args.ctx, args.layers)
+    # per-GPU algorithmic bytes: matrices and KV shard by tp; gains and the embedding row are replicated
+    bytes_w = (args.layers * 2 * (4 * E * E + 3 * E * F) + 2 * V * E) // world + (2 * args.layers + 1) * 4 * E + 2 * E
+    bytes_total = bytes_w + kv_bytes(args.ctx, args.layers) // world
     achieved = bytes_total / (ms_step * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "decode_kernel_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    roof = {"bound": "hbm", "kernel": "decode_kernel (persistent, 1 launch per token)", "achieved": achieved, "peak": peak,
+    roof = {"bound": "hbm", "kernel": "decode_kernel (persistent, 1 launch per token per GPU)", "achieved": achieved, "per_gpu": True, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bytes_total, "weights_only_GBps": bytes_w / (ms_step * 1e-3) / 1e9,
             "frac_of_8TBps_spec": achieved / 8000.0}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.ctx)
 
     line = {"metric": "tokens/sec LLaMA-7B f16 single-token decode; achieved HBM GB/s vs roofline", "value": tok_s, "unit": "tokens/s",
@@ -253,12 +266,15 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"LLaMA-7B f16, 1-token decode, ctx={args.ctx} (n_past={n_past}), 1xB200", "n_layer": args.layers,
                        "l2": "inputs (13.2 GB weights + 0.5 GB KV per step) exceed the 126 MB L2; no flush needed",
-                       "kv": "f32, synthetic fill for positions < n_past", "parallelism": "single GPU"},
+                       "kv": "f32, synthetic fill for positions < n_past",
+                       "parallelism": "single GPU" if world == 1 else f"tp{world}: row/column-sharded matvecs, in-kernel one-shot all-reduce over NVLink peer memory (2 per layer)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roof, "cpu_baseline": cpu}
     if args.layers != L:
         line["invalid"] = "debug run with fewer layers"
     if rank == 0:
         print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
     model.close()
 
 

@@ -101,6 +101,7 @@ struct LlamaModel {                  // th-llama.hpp:100-177
     float* pinnedLogits = nullptr;
     std::vector<float> lastLogits;
     int64_t gpuLaunches = 0;         // kernels launched by the last th_eval_gpu call
+    int32_t tp_rank = 0, tp_size = 1; // tensor parallel: this model holds rank tp_rank's shard (fused path only)
 
     ~LlamaModel();
 };
@@ -122,6 +123,11 @@ void build_final_compute_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, s
 // evaluated as n_tokens consecutive single-token steps (logits of the last one are kept).
 tk_llama_token th_eval_gpu(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens,
                            int n_tokens, int n_past);
+// The two halves of th_eval_gpu (enqueue / wait + read back + sample), exposed so one host thread can drive
+// several tensor-parallel ranks: launch all of them, then finish all of them.
+int th_eval_gpu_launch(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens, int n_tokens,
+                       int n_past);
+tk_llama_token th_eval_gpu_finish(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m);
 // greedy branch of th-llama.cpp:814-838
 tk_llama_token llama_sample_top_p_top_k(std::shared_ptr<LlamaModel> m, const std::vector<tk_llama_token>& last_n_tokens, int top_k,
                                         float top_p, float temp, float repeat_penalty, std::vector<float>& logits);

@@ -60,6 +60,14 @@ int  thk_sync(thk_ctx* ctx);
 int  thk_host_alloc(thk_ctx* ctx, size_t bytes, void** hptr);
 int  thk_host_free(thk_ctx* ctx, void* hptr);
 
+/* ---- mapping device memory across ranks (tensor parallel wiring; no reference analogue) ----
+ * thk_ipc_export/import wrap cudaIpcGetMemHandle/OpenMemHandle (64-byte handle) for one-process-per-GPU
+ * launches; thk_enable_peer_access is the same-process equivalent. */
+int  thk_ipc_export(thk_ctx* ctx, void* dptr, unsigned char* handle64);
+int  thk_ipc_import(thk_ctx* ctx, const unsigned char* handle64, void** dptr);
+int  thk_ipc_close(thk_ctx* ctx, void* dptr);
+int  thk_enable_peer_access(thk_ctx* ctx, thk_ctx* peer);
+
 /* ---- the reference's 32-byte uniform blocks (th-llama.hpp:181-217), device resident ---- */
 typedef struct { uint32_t n_past, n_tokens; float pad2, pad3; uint32_t pad4[4]; } thk_network_uniforms;
 typedef struct { uint32_t A_B, A_M, A_N; float scale; uint32_t B_B, B_M, B_N; float offset; } thk_dims_uniforms;

@@ -90,6 +90,10 @@ def kernels() -> C.CDLL:
             "thk_decoder_exchange_info": [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t)],
             "thk_decoder_set_peers": [vp, C.POINTER(vp), C.POINTER(vp), C.c_int],
             "thk_gemm_f16_tc": [vp, vp, vp, vp, i64, i64, i64],
+            "thk_ipc_export": [vp, vp, C.POINTER(C.c_ubyte)],
+            "thk_ipc_import": [vp, C.POINTER(C.c_ubyte), C.POINTER(vp)],
+            "thk_ipc_close": [vp, vp],
+            "thk_enable_peer_access": [vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(K, name)
@@ -114,6 +118,15 @@ def host() -> C.CDLL:
         H.capi_device_destroy.argtypes = [vp]
         H.capi_model_synthetic.restype = vp
         H.capi_model_synthetic.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u64]
+        H.capi_model_synthetic_tp.restype = vp
+        H.capi_model_synthetic_tp.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u64, C.c_int, C.c_int]
+        H.capi_model_load_tp.restype = vp
+        H.capi_model_load_tp.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        H.capi_model_tp.argtypes = [vp, i32p]
+        H.capi_exchange_info.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        H.capi_set_peers.argtypes = [vp, C.POINTER(vp), C.c_int]
+        H.capi_eval_launch.argtypes = [vp, i32p, C.c_int, C.c_int]
+        H.capi_eval_finish.argtypes = [vp, f32p]
         H.capi_model_load.restype = vp
         H.capi_model_load.argtypes = [vp, C.c_char_p, C.c_int]
         H.capi_model_free.argtypes = [vp]
@@ -235,14 +248,43 @@ class LlamaModel:
         host().capi_model_dims(handle, d)
         (self.n_vocab, self.n_embd, self.n_mult, self.n_head, self.n_layer, self.n_ctx, self.n_ff,
          self.has_fused, self.eval_path) = list(d)
+        t = (C.c_int32 * 2)()
+        host().capi_model_tp(handle, t)
+        self.tp_rank, self.tp_size = t[0], t[1]
+        self.n_vocab_local = self.n_vocab // self.tp_size
 
     @classmethod
-    def synthetic(cls, dev: Device, n_vocab=32000, n_embd=4096, n_mult=256, n_head=32, n_layer=32, n_ctx=512, seed=0x7B5EED):
-        return cls(dev, host().capi_model_synthetic(dev.h, n_vocab, n_embd, n_mult, n_head, n_layer, n_ctx, seed))
+    def synthetic(cls, dev: Device, n_vocab=32000, n_embd=4096, n_mult=256, n_head=32, n_layer=32, n_ctx=512, seed=0x7B5EED,
+                  tp_rank=0, tp_size=1):
+        return cls(dev, host().capi_model_synthetic_tp(dev.h, n_vocab, n_embd, n_mult, n_head, n_layer, n_ctx, seed, tp_rank, tp_size))
 
     @classmethod
-    def load(cls, dev: Device, path: str, n_ctx: int = 512):
-        return cls(dev, host().capi_model_load(dev.h, path.encode(), n_ctx))
+    def load(cls, dev: Device, path: str, n_ctx: int = 512, tp_rank=0, tp_size=1):
+        return cls(dev, host().capi_model_load_tp(dev.h, path.encode(), n_ctx, tp_rank, tp_size))
+
+    # ---- tensor-parallel wiring (token_hawk_b200.tp) ----
+    def exchange_info(self):
+        p, n = vp(), u64()
+        if host().capi_exchange_info(self.h, C.byref(p), C.byref(n)):
+            raise ThkError(-1, host().capi_last_error().decode())
+        return p.value, n.value
+
+    def set_peers(self, ptrs):
+        arr = (vp * len(ptrs))(*[vp(x) for x in ptrs])
+        if host().capi_set_peers(self.h, arr, len(ptrs)):
+            raise ThkError(-1, host().capi_last_error().decode())
+
+    def eval_launch(self, tokens, n_past: int):
+        toks = np.ascontiguousarray(np.asarray(tokens, np.int32).reshape(-1))
+        if host().capi_eval_launch(self.h, toks.ctypes.data_as(i32p), len(toks), n_past):
+            raise ThkError(-1, host().capi_last_error().decode())
+
+    def eval_finish(self):
+        logits = np.empty(self.n_vocab_local, np.float32)
+        tok = host().capi_eval_finish(self.h, logits.ctypes.data_as(f32p))
+        if tok < 0:
+            raise ThkError(tok, host().capi_last_error().decode())
+        return tok, logits
 
     def close(self):
         if self.h:
@@ -257,7 +299,7 @@ class LlamaModel:
     def eval(self, tokens, n_past: int, want_logits: bool = True):
         """th_eval_gpu: host token ids in, (greedy token, host logits) out."""
         toks = np.ascontiguousarray(np.asarray(tokens, np.int32).reshape(-1))
-        logits = np.empty(self.n_vocab, np.float32) if want_logits else None
+        logits = np.empty(self.n_vocab_local, np.float32) if want_logits else None
         tok = host().capi_eval(self.h, toks.ctypes.data_as(i32p), len(toks), n_past,
                                logits.ctypes.data_as(f32p) if want_logits else None)
         if tok < 0:
@@ -279,7 +321,7 @@ class LlamaModel:
 
     def generate_device(self, first_token: int, n_past: int, n_steps: int, want_logits=False):
         out = np.empty(n_steps, np.int32)
-        logits = np.empty(self.n_vocab, np.float32) if want_logits else None
+        logits = np.empty(self.n_vocab_local, np.float32) if want_logits else None
         rc = host().capi_generate_device(self.h, first_token, n_past, n_steps, out.ctypes.data_as(i32p),
                                          logits.ctypes.data_as(f32p) if want_logits else None)
         if rc:

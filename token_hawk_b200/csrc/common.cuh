@@ -18,6 +18,9 @@ struct thk_ctx {
 
 void thk_set_error(const char* fmt, ...);
 
+// every entry point makes its context's device current (several contexts may live in one process)
+#define THK_ENTER(ctx) do { if (ctx) cudaSetDevice((ctx)->device); } while (0)
+
 #define THK_CHECK_ARG(cond, ...)                                    \
     do {                                                            \
         if (!(cond)) { thk_set_error(__VA_ARGS__); return THK_E_INVALID; } \

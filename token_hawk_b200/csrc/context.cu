@@ -57,6 +57,7 @@ extern "C" int thk_init_on_stream(int device, void* stream, thk_ctx** out) {
     return init_common(device, (cudaStream_t)stream, false, out);
 }
 extern "C" int thk_destroy(thk_ctx* ctx) {
+    THK_ENTER(ctx);
     if (!ctx) return THK_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
@@ -64,6 +65,7 @@ extern "C" int thk_destroy(thk_ctx* ctx) {
     return THK_OK;
 }
 extern "C" int thk_device_info(thk_ctx* ctx, int* sm, int* maj, int* min, size_t* mem) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx, "thk_device_info: null ctx");
     if (sm) *sm = ctx->sm_count;
     if (maj) *maj = ctx->cc_major;
@@ -74,6 +76,7 @@ extern "C" int thk_device_info(thk_ctx* ctx, int* sm, int* maj, int* min, size_t
 extern "C" void* thk_stream(thk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 extern "C" int thk_malloc(thk_ctx* ctx, size_t bytes, void** dptr) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && dptr, "thk_malloc: null argument");
     *dptr = nullptr;
     THK_CUDA(cudaSetDevice(ctx->device));
@@ -81,6 +84,7 @@ extern "C" int thk_malloc(thk_ctx* ctx, size_t bytes, void** dptr) {
     return THK_OK;
 }
 extern "C" int thk_free(thk_ctx* ctx, void* dptr) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx, "thk_free: null ctx");
     if (!dptr) return THK_OK;
     THK_CUDA(cudaSetDevice(ctx->device));
@@ -88,38 +92,86 @@ extern "C" int thk_free(thk_ctx* ctx, void* dptr) {
     return THK_OK;
 }
 extern "C" int thk_memset(thk_ctx* ctx, void* dptr, int value, size_t bytes) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && dptr, "thk_memset: null argument");
     THK_CUDA(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
     return THK_OK;
 }
 extern "C" int thk_upload(thk_ctx* ctx, void* dst, size_t off, const void* src, size_t bytes) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && dst && src, "thk_upload: null argument");
     THK_CUDA(cudaMemcpyAsync((char*)dst + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return THK_OK;
 }
 extern "C" int thk_download(thk_ctx* ctx, void* dst, const void* src, size_t off, size_t bytes) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && dst && src, "thk_download: null argument");
     THK_CUDA(cudaMemcpyAsync(dst, (const char*)src + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     THK_CUDA(cudaStreamSynchronize(ctx->stream));
     return THK_OK;
 }
 extern "C" int thk_copy(thk_ctx* ctx, void* dst, size_t doff, const void* src, size_t soff, size_t bytes) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && dst && src, "thk_copy: null argument");
     THK_CUDA(cudaMemcpyAsync((char*)dst + doff, (const char*)src + soff, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return THK_OK;
 }
 extern "C" int thk_sync(thk_ctx* ctx) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx, "thk_sync: null ctx");
     THK_CUDA(cudaStreamSynchronize(ctx->stream));
     return THK_OK;
 }
 extern "C" int thk_host_alloc(thk_ctx* ctx, size_t bytes, void** hptr) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && hptr, "thk_host_alloc: null argument");
     THK_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
     return THK_OK;
 }
 extern "C" int thk_host_free(thk_ctx* ctx, void* hptr) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx, "thk_host_free: null ctx");
     if (hptr) THK_CUDA(cudaFreeHost(hptr));
+    return THK_OK;
+}
+
+// ---- cross-process / cross-device mapping of exchange regions (tensor parallel wiring) ----
+extern "C" int thk_ipc_export(thk_ctx* ctx, void* dptr, unsigned char* handle64) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx && dptr && handle64, "thk_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    THK_CUDA(cudaSetDevice(ctx->device));
+    THK_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, 64);
+    return THK_OK;
+}
+extern "C" int thk_ipc_import(thk_ctx* ctx, const unsigned char* handle64, void** dptr) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx && handle64 && dptr, "thk_ipc_import: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    THK_CUDA(cudaSetDevice(ctx->device));
+    THK_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return THK_OK;
+}
+extern "C" int thk_ipc_close(thk_ctx* ctx, void* dptr) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx, "thk_ipc_close: null ctx");
+    if (dptr) THK_CUDA(cudaIpcCloseMemHandle(dptr));
+    return THK_OK;
+}
+// same-process multi-GPU: let `ctx`'s device read/write memory of `peer`'s device
+extern "C" int thk_enable_peer_access(thk_ctx* ctx, thk_ctx* peer) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx && peer, "thk_enable_peer_access: null argument");
+    if (ctx->device == peer->device) return THK_OK;
+    int can = 0;
+    THK_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+    if (!can) { thk_set_error("device %d cannot access device %d", ctx->device, peer->device); return THK_E_UNSUPPORTED; }
+    THK_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { thk_set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return THK_E_CUDA; }
+    cudaGetLastError();
     return THK_OK;
 }

@@ -75,6 +75,11 @@ struct DecParams {
     int att_tpos;                       // positions per attention tile
     int att_max_split;
     unsigned long long timeout_ns;
+    // tensor parallel exchange (tp_size > 1): every rank owns one region laid out as
+    //   float xb[2][tp][n_embd] | float amax_val[tp] | int amax_idx[tp] | unsigned flags[tp] | unsigned flags2[tp]
+    // and writes its partial vectors / argmax candidates straight into every peer's region over NVLink.
+    unsigned char* xchg[8];             // region base per rank (peer-mapped pointers; [tp_rank] is local)
+    unsigned epoch_base;                // flags are monotonic: exchange k of this launch uses epoch_base + k + 1
     unsigned long long* prof;           // optional timeline: [cta][phase<256][8] u64 (see prof_mark), then [cta][4] producer stats
 };
 
@@ -125,6 +130,25 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// exchange region accessors
+__device__ __forceinline__ float* xb_ptr(const DecParams& p, int rank, int which, int src) {
+    return (float*)p.xchg[rank] + ((size_t)which * p.tp_size + src) * p.n_embd;
+}
+__device__ __forceinline__ size_t xchg_tail(const DecParams& p) { return (size_t)2 * p.tp_size * p.n_embd * sizeof(float); }
+__device__ __forceinline__ float* xamax_val(const DecParams& p, int rank) { return (float*)(p.xchg[rank] + xchg_tail(p)); }
+__device__ __forceinline__ int* xamax_idx(const DecParams& p, int rank) { return (int*)(p.xchg[rank] + xchg_tail(p)) + p.tp_size; }
+__device__ __forceinline__ unsigned* xflags(const DecParams& p, int rank, int set) {
+    return (unsigned*)(p.xchg[rank] + xchg_tail(p)) + (2 + set) * p.tp_size;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* ptr, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* ptr) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
 
 constexpr int kProfPhases = 256;
 enum ProfSlot { PROF_START = 0, PROF_PROLOGUE = 1, PROF_FIRST_TILE = 2, PROF_LAST_TILE = 3, PROF_ARRIVE = 4, PROF_FENCED = 5, PROF_WAIT_FULL = 6 };
@@ -332,20 +356,39 @@ __device__ __forceinline__ void prof_mark(const Cons& c, int slot) {
 // Grid-wide barrier between data-dependent phases.  Every math and epilogue thread has issued its
 // global writes; bar.sync orders them before thread 0's gpu-scope release (cumulativity), and the
 // acquire + second bar.sync make the other CTAs' writes visible to all threads here (read with .cg).
-__device__ __forceinline__ void grid_barrier(Cons& c) {
+__device__ __forceinline__ void grid_barrier(Cons& c, int xset = -1, unsigned epoch = 0u) {
     prof_mark(c, PROF_ARRIVE);
     bar_sync(BAR_ALL, kMathThreads + 32);
     ++c.nbar;
     if (c.ct == 0) {
         red_release_add(c.p.bar_ctr, 1u);
         const unsigned target = c.nbar * gridDim.x;
-        if (ld_acquire_u32(c.p.bar_ctr) < target) {
-            const unsigned long long t0 = gtimer();
-            unsigned it = 0;
-            while (ld_acquire_u32(c.p.bar_ctr) < target) {
-                if ((++it & 63u) == 0u) {
-                    if (aborted(c.p)) break;
-                    if (gtimer() - t0 > c.p.timeout_ns) { raise_abort(c.p, 0x200u, c.nbar, target); break; }
+        unsigned long long t0 = 0;
+        unsigned it = 0;
+        while (ld_acquire_u32(c.p.bar_ctr) < target) {
+            if ((++it & 63u) == 0u) {
+                if (t0 == 0) t0 = gtimer();
+                if (aborted(c.p)) break;
+                if (gtimer() - t0 > c.p.timeout_ns) { raise_abort(c.p, 0x200u, c.nbar, target); break; }
+            }
+        }
+        if (xset >= 0) {
+            // Cross-GPU step of the one-shot all-reduce: every local CTA has pushed its partial rows into all
+            // peers (system-scope fenced before arriving here); rank-level flag tells the peers "my part is in".
+            const DecParams& p = c.p;
+            if (blockIdx.x == 0) {
+                __threadfence_system();
+                for (int d = 0; d < p.tp_size; ++d) st_release_sys(xflags(p, d, xset) + p.tp_rank, epoch);
+            }
+            t0 = 0; it = 0;
+            for (int src = 0; src < p.tp_size; ++src) {
+                const unsigned* f = xflags(p, p.tp_rank, xset) + src;
+                while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+                    if ((++it & 63u) == 0u) {
+                        if (t0 == 0) t0 = gtimer();
+                        if (aborted(p)) break;
+                        if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x400u, (unsigned)src, epoch); break; }
+                    }
                 }
             }
         }
@@ -359,8 +402,21 @@ __device__ __forceinline__ void prefetch_l2(const void* base, int bytes, int tid
         asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)base + off));
 }
 
-// xs <- rmsnorm(src) * gain   (cmdbuf_rms_norm + cmdbuf_row_element_multiply, th.cpp:1153-1200,1298-1315)
-__device__ __forceinline__ void prologue_norm(Cons& c, const float* src, const float* gain, int n) {
+// xs <- rmsnorm(v) * gain with v = src (+ the tp partial vectors of exchange `which`, in rank order)
+// (cmdbuf_rms_norm + cmdbuf_row_element_multiply, th.cpp:1153-1200,1298-1315; the residual adds of
+// th-llama.cpp:409/447 move here under tensor parallelism).  When `out` is given, v is also written
+// back as the new residual stream, each float4 by exactly one CTA.
+__device__ __forceinline__ float4 load_summed(const DecParams& p, const float* src, int which, int i) {
+    float4 v = __ldcg((const float4*)(src + i));
+    if (which >= 0) {
+        for (int r = 0; r < p.tp_size; ++r) {
+            const float4 a = __ldcg((const float4*)(xb_ptr(p, p.tp_rank, which, r) + i));
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
+    }
+    return v;
+}
+__device__ __forceinline__ void prologue_norm(Cons& c, const float* src, const float* gain, int n, int which = -1, float* out = nullptr) {
     constexpr int kHold = 4;                         // float4s kept in registers per thread (n <= 4096)
     float4 v[kHold], g[kHold];
     float ss = 0.f;
@@ -369,7 +425,7 @@ __device__ __forceinline__ void prologue_norm(Cons& c, const float* src, const f
 #pragma unroll
         for (int k = 0; k < kHold; ++k) {
             const int i = (c.ct + k * kMathThreads) * 4;
-            if (i < n) { v[k] = __ldcg((const float4*)(src + i)); g[k] = __ldg((const float4*)(gain + i)); }
+            if (i < n) { v[k] = load_summed(c.p, src, which, i); g[k] = __ldg((const float4*)(gain + i)); }
         }
 #pragma unroll
         for (int k = 0; k < kHold; ++k) {
@@ -378,7 +434,7 @@ __device__ __forceinline__ void prologue_norm(Cons& c, const float* src, const f
         }
     } else {
         for (int i = c.ct * 4; i < n; i += kMathThreads * 4) {
-            const float4 t = __ldcg((const float4*)(src + i));
+            const float4 t = load_summed(c.p, src, which, i);
             ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
         }
     }
@@ -397,15 +453,17 @@ __device__ __forceinline__ void prologue_norm(Cons& c, const float* src, const f
                 float4 o;
                 o.x = (v[k].x * inv) * g[k].x; o.y = (v[k].y * inv) * g[k].y; o.z = (v[k].z * inv) * g[k].z; o.w = (v[k].w * inv) * g[k].w;
                 *(float4*)(c.xs + xs_index(i)) = o;
+                if (out && (unsigned)(i >> 2) % gridDim.x == blockIdx.x) *(float4*)(out + i) = v[k];
             }
         }
     } else {
         for (int i = c.ct * 4; i < n; i += kMathThreads * 4) {
-            const float4 t = __ldcg((const float4*)(src + i));
+            const float4 t = load_summed(c.p, src, which, i);
             const float4 gg = __ldg((const float4*)(gain + i));
             float4 o;
             o.x = (t.x * inv) * gg.x; o.y = (t.y * inv) * gg.y; o.z = (t.z * inv) * gg.z; o.w = (t.w * inv) * gg.w;
             *(float4*)(c.xs + xs_index(i)) = o;
+            if (out && (unsigned)(i >> 2) % gridDim.x == blockIdx.x) *(float4*)(out + i) = t;
         }
     }
     bar_sync(BAR_MATH, kMathThreads);
@@ -552,7 +610,7 @@ __device__ __forceinline__ void epi_mat_phase(Cons& c, const PhaseDesc& d, EpiKi
             const int row0 = lg * d.RT;
             const int nrows = min(d.RT, d.rows[si] - row0);
             float resid[2] = {0.f, 0.f};
-            if (kind == EPI_WO || kind == EPI_W2) {               // residual operand: load before waiting for the sums
+            if ((kind == EPI_WO || kind == EPI_W2) && p.tp_size == 1) {   // residual operand: load before waiting for the sums
                 const float* rs = (kind == EPI_WO) ? p.x : p.h1;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) { const int t = c.lane + 32 * k; if (t < nrows) resid[k] = __ldcg(rs + row0 + t); }
@@ -582,12 +640,18 @@ __device__ __forceinline__ void epi_mat_phase(Cons& c, const PhaseDesc& d, EpiKi
                         }
                     }
                     break;
-                case EPI_WO: p.h1[r] = resid[k] + y; break;                            // th-llama.cpp:409
+                case EPI_WO:                                                           // th-llama.cpp:409
+                    if (p.tp_size == 1) p.h1[r] = resid[k] + y;
+                    else for (int dst = 0; dst < p.tp_size; ++dst) xb_ptr(p, dst, 0, p.tp_rank)[r] = y;   // partial -> every rank
+                    break;
                 case EPI_W13:
                     if (sub == 0) es.gate[k] = y;
                     else { const float gv = es.gate[k]; p.ff[r] = (gv / (1.0f + expf(-gv))) * y; }   // :436,:438
                     break;
-                case EPI_W2: p.x[r] = resid[k] + y; break;                             // th-llama.cpp:447
+                case EPI_W2:                                                           // th-llama.cpp:447
+                    if (p.tp_size == 1) p.x[r] = resid[k] + y;
+                    else for (int dst = 0; dst < p.tp_size; ++dst) xb_ptr(p, dst, 1, p.tp_rank)[r] = y;
+                    break;
                 case EPI_OUT: {
                     if (p.logits) p.logits[r] = y;
                     const int gid = p.tp_rank * p.Vl + r;
@@ -682,12 +746,30 @@ __device__ __forceinline__ void math_att_phase(Cons& c, const thk_llama_layer& L
             const float corr = expf(m - m_new);
             lsum *= corr; o4.x *= corr; o4.y *= corr; o4.z *= corr; o4.w *= corr;
             m = m_new;
+            bar_sync(BAR_MATH, kMathThreads);                  // everyone has read the raw scores
+            for (int j = c.ct; j < np; j += kMathThreads) c.sm->sc[buf][j] = expf(c.sm->sc[buf][j] - m);   // one exp per position
+            bar_sync(BAR_MATH, kMathThreads);
             // V tile -> weighted sum
             if (c.ok) c.ok = mbar_wait(p, c.ring.full_bar(), c.ring.full_parity(), 5);
             if (c.ok) {
                 const float* vt = (const float*)(c.slots + (size_t)c.ring.slot() * kSlotBytes);
-                for (int j = c.cw; j < np; j += kMathWarps) {
-                    const float pj = expf(c.sm->sc[buf][j] - m);
+                int j = c.cw;
+                for (; j + 3 * kMathWarps < np; j += 4 * kMathWarps) {     // 4 positions in flight
+                    float pj[4]; float4 v4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        pj[u] = c.sm->sc[buf][j + u * kMathWarps];
+                        v4[u] = act ? *(const float4*)(vt + (j + u * kMathWarps) * D + c.lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        lsum += pj[u];
+                        o4.x = fmaf(pj[u], v4[u].x, o4.x); o4.y = fmaf(pj[u], v4[u].y, o4.y);
+                        o4.z = fmaf(pj[u], v4[u].z, o4.z); o4.w = fmaf(pj[u], v4[u].w, o4.w);
+                    }
+                }
+                for (; j < np; j += kMathWarps) {
+                    const float pj = c.sm->sc[buf][j];
                     lsum += pj;
                     if (act) {
                         const float4 v4 = *(const float4*)(vt + j * D + c.lane * 4);
@@ -785,14 +867,16 @@ __device__ __forceinline__ Cons cons_from(const DecParams& p, const Shared& S, c
 }
 __device__ __forceinline__ MState state_of(const Cons& c) { return MState{c.ring.tc, c.ok ? 1 : 0, c.nbar, c.ring.wait_cyc}; }
 
-__device__ __noinline__ MState nl_grid_barrier(const DecParams& p, Shared S, MState st, int epi) {
+__device__ __noinline__ MState nl_grid_barrier(const DecParams& p, Shared S, MState st, int epi, int xset = -1, unsigned epoch = 0u) {
     Cons c = cons_from(p, S, st, epi != 0);
-    grid_barrier(c);
+    if (epi && xset >= 0) __threadfence_system();      // this warp's pushes to the peers are visible system-wide
+    grid_barrier(c, xset, epoch);
     return state_of(c);
 }
-__device__ __noinline__ MState nl_prologue_norm(const DecParams& p, Shared S, MState st, const float* src, const float* gain, int n) {
+__device__ __noinline__ MState nl_prologue_norm(const DecParams& p, Shared S, MState st, const float* src, const float* gain, int n,
+                                                int which = -1, float* out = nullptr) {
     Cons c = cons_from(p, S, st, false);
-    prologue_norm(c, src, gain, n);
+    prologue_norm(c, src, gain, n, which, out);
     return state_of(c);
 }
 __device__ __noinline__ MState nl_prologue_copy(const DecParams& p, Shared S, MState st, const float* src, int n) {
@@ -840,13 +924,22 @@ __device__ void math_main(const DecParams& p, Shared S) {
     }
     st = nl_grid_barrier(p, S, st, 0);
     const int nsteps = 5 * p.n_layer + 1;
+    const bool tp = p.tp_size > 1;
+    unsigned xk = 0;                                       // cross-GPU exchanges done in this launch
     int l = 0, k = K_QKV;
     for (int i = 0; i < nsteps; ++i) {
         const thk_llama_layer* L = p.layers + (l < p.n_layer ? l : p.n_layer - 1);
         if (k == K_QKV || k == K_W13 || k == K_OUT) {
-            const float* src = (k == K_W13) ? p.h1 : p.x;
             const float* gain = (k == K_QKV) ? L->attention_norm : (k == K_W13) ? L->ffn_norm : p.norm;
-            st = nl_prologue_norm(p, S, st, src, gain, p.n_embd);
+            if (!tp) {
+                st = nl_prologue_norm(p, S, st, (k == K_W13) ? p.h1 : p.x, gain, p.n_embd);
+            } else if (k == K_W13) {
+                st = nl_prologue_norm(p, S, st, p.x, gain, p.n_embd, 0, p.h1);         // h1 = x + sum of Wo partials
+            } else if (i == 0) {
+                st = nl_prologue_norm(p, S, st, p.x, gain, p.n_embd);                    // first layer: x is the embedding
+            } else {
+                st = nl_prologue_norm(p, S, st, p.h1, gain, p.n_embd, 1, p.x);         // x = h1 + sum of W2 partials
+            }
         } else if (k == K_WO || k == K_W2) {
             st = nl_prologue_copy(p, S, st, k == K_WO ? p.o : p.ff, k == K_WO ? p.Eh : p.Fh);
         }
@@ -854,7 +947,8 @@ __device__ void math_main(const DecParams& p, Shared S) {
         else st = math_mat(p, S, st, phase_of(k));
         if (k == K_WO) prefetch_l2(L->ffn_norm, p.n_embd * 4, tid, kMathThreads);
         if (k == K_W2) prefetch_l2(l + 1 < p.n_layer ? p.layers[l + 1].attention_norm : p.norm, p.n_embd * 4, tid, kMathThreads);
-        if (k != K_OUT || p.next_token || p.next_logit) st = nl_grid_barrier(p, S, st, 0);
+        if (tp && (k == K_WO || k == K_W2)) { ++xk; st = nl_grid_barrier(p, S, st, 0, 0, p.epoch_base + xk); }
+        else if (k != K_OUT || p.next_token || p.next_logit) st = nl_grid_barrier(p, S, st, 0);
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
     }
 }
@@ -873,6 +967,7 @@ __device__ void epi_main(const DecParams& p, Shared S) {
     __syncwarp();
     st = nl_grid_barrier(p, S, st, 1);
     const int nsteps = 5 * p.n_layer + 1;
+    unsigned xk = 0;
     int l = 0, k = K_QKV;
     for (int i = 0; i < nsteps; ++i) {
         if (k != K_ATT) {
@@ -881,7 +976,8 @@ __device__ void epi_main(const DecParams& p, Shared S) {
             st = r.st; es = r.es;
         }
         if (k == K_OUT) break;
-        st = nl_grid_barrier(p, S, st, 1);
+        if (p.tp_size > 1 && (k == K_WO || k == K_W2)) { ++xk; st = nl_grid_barrier(p, S, st, 1, 0, p.epoch_base + xk); }
+        else st = nl_grid_barrier(p, S, st, 1);
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
     }
     if (p.next_token || p.next_logit) {
@@ -902,6 +998,28 @@ __device__ void epi_main(const DecParams& p, Shared S) {
                 if (idx < 0) continue;
                 const float v = __ldcg(p.amax_val + b);
                 if (gi < 0 || v > gv || (v == gv && idx < gi)) { gv = v; gi = idx; }
+            }
+            if (p.tp_size > 1) {
+                // cross-rank argmax: push this rank's candidate to every rank, wait for all, lowest id wins ties
+                const unsigned epoch = p.epoch_base + 2u * (unsigned)p.n_layer + 1u;
+                for (int d = 0; d < p.tp_size; ++d) { xamax_val(p, d)[p.tp_rank] = gv; xamax_idx(p, d)[p.tp_rank] = gi; }
+                __threadfence_system();
+                for (int d = 0; d < p.tp_size; ++d) st_release_sys(xflags(p, d, 1) + p.tp_rank, epoch);
+                unsigned long long t0 = 0; unsigned it = 0;
+                gv = 0.f; gi = -1;
+                for (int src = 0; src < p.tp_size; ++src) {
+                    const unsigned* f = xflags(p, p.tp_rank, 1) + src;
+                    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+                        if ((++it & 63u) == 0u) {
+                            if (t0 == 0) t0 = gtimer();
+                            if (aborted(p)) break;
+                            if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x401u, (unsigned)src, epoch); break; }
+                        }
+                    }
+                    const int idx = __ldcv(xamax_idx(p, p.tp_rank) + src);
+                    const float v = __ldcv(xamax_val(p, p.tp_rank) + src);
+                    if (idx >= 0 && (gi < 0 || v > gv || (v == gv && idx < gi))) { gv = v; gi = idx; }
+                }
             }
             if (p.next_token) *p.next_token = gi < 0 ? 0 : gi;
             if (p.next_logit) *p.next_logit = gv;
@@ -951,7 +1069,7 @@ PhaseDesc make_phase(int nseg, const int* rows, int C, bool paired, int n_cta) {
         if (opts[i][1] > cap) break;
         RPW = opts[i][0]; CPW = opts[i][1];
         const int G = (rows_total + WR * RPW - 1) / (WR * RPW);
-        if (G >= 8 * n_cta) break;
+        if (G >= 2 * n_cta) break;      // prefer the widest row group: it streams at the HBM rate
     }
     d.WC = WC; d.RPW = RPW; d.CPW = CPW;
     d.RT = WR * RPW;
@@ -982,10 +1100,15 @@ struct thk_decoder {
     int grid = 0;
     size_t smem = 0;
     int last_launches = 0;
+    unsigned char* xchg = nullptr;      // tensor-parallel exchange region (local)
+    size_t xchg_bytes = 0;
+    unsigned epoch = 0;
+    bool peers_set = false;
     unsigned long long* d_prof = nullptr;
 };
 
 static int check_status(thk_decoder* d) {
+    THK_ENTER(d->ctx);
     unsigned st[4];
     THK_CUDA(cudaMemcpyAsync(st, d->p.status, sizeof st, cudaMemcpyDeviceToHost, d->ctx->stream));
     THK_CUDA(cudaStreamSynchronize(d->ctx->stream));
@@ -1004,7 +1127,7 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     THK_CHECK_ARG(ctx && dims && layers && tok_embeddings && norm && output && out, "thk_decoder_create: null argument");
     *out = nullptr;
     const int tp = dims->tp_size > 0 ? dims->tp_size : 1;
-    THK_CHECK_ARG(tp == 1, "thk_decoder_create: tensor parallel sizes > 1 go through thk_decoder_create + set_peers (not built yet)");
+    THK_CHECK_ARG(tp <= 8 && dims->tp_rank >= 0 && dims->tp_rank < tp, "thk_decoder_create: tp_size %d / tp_rank %d unsupported (1..8)", tp, dims->tp_rank);
     THK_CHECK_ARG(dims->n_embd > 0 && dims->n_head > 0 && dims->n_embd % dims->n_head == 0, "bad n_embd/n_head");
     const int D = dims->n_embd / dims->n_head;
     THK_CHECK_ARG(D % 4 == 0 && D <= kMaxHeadDim && D % 2 == 0, "head_dim %d unsupported (need multiple of 4, <= %d)", D, kMaxHeadDim);
@@ -1061,6 +1184,13 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     p.head_ctr = d->ctrl + 64;
     p.status = d->ctrl + 64 + p.Hl;
     THK_CUDA(cudaMalloc(&d->d_tok, sizeof(int) * 2));
+    if (tp > 1) {
+        d->xchg_bytes = ((size_t)2 * tp * p.n_embd * sizeof(float) + (size_t)4 * tp * sizeof(unsigned) + 255) & ~(size_t)255;
+        THK_CUDA(cudaMalloc(&d->xchg, d->xchg_bytes));
+        THK_CUDA(cudaMemset(d->xchg, 0, d->xchg_bytes));
+        p.xchg[p.tp_rank] = d->xchg;
+    }
+    THK_CUDA(cudaDeviceSynchronize());
     *out = d;
     return THK_OK;
 }
@@ -1069,14 +1199,20 @@ extern "C" int thk_decoder_destroy(thk_decoder* d) {
     if (!d) return THK_OK;
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
-    cudaFree(d->d_layers); cudaFree(d->scratch); cudaFree(d->ctrl); cudaFree(d->d_tok); cudaFree(d->d_prof);
+    cudaFree(d->d_layers); cudaFree(d->scratch); cudaFree(d->ctrl); cudaFree(d->d_tok); cudaFree(d->d_prof); cudaFree(d->xchg);
     delete d;
     return THK_OK;
 }
 
 static int launch_step(thk_decoder* d, const int32_t* token, int32_t n_past, float* logits, int32_t* next_token, float* next_logit) {
+    THK_ENTER(d->ctx);
     DecParams p = d->p;
     p.token = token; p.n_past = n_past; p.logits = logits; p.next_token = next_token; p.next_logit = next_logit;
+    if (p.tp_size > 1) {
+        if (!d->peers_set) { thk_set_error("thk_decoder_step: tensor-parallel decoder has no peers (call thk_decoder_set_peers)"); return THK_E_INVALID; }
+        p.epoch_base = d->epoch;
+        d->epoch += 2u * (unsigned)p.n_layer + 2u;
+    }
     p.bar_ctr = d->ctrl + (d->launch_seq % 64);
     p.bar_next = d->ctrl + ((d->launch_seq + 1) % 64);
     ++d->launch_seq;
@@ -1105,7 +1241,6 @@ extern "C" int thk_decoder_step(thk_decoder* d, const int32_t* token, int32_t n_
 extern "C" int thk_decoder_generate(thk_decoder* d, const int32_t* first_token, int32_t n_past, int32_t n_steps,
                                     int32_t* tokens_out, float* last_logits) {
     THK_CHECK_ARG(d && first_token && tokens_out && n_steps > 0, "thk_decoder_generate: bad argument");
-    THK_CHECK_ARG(d->p.tp_size == 1, "thk_decoder_generate: single-GPU only");
     THK_CHECK_ARG(n_past >= 0 && n_past + n_steps <= d->p.n_ctx, "thk_decoder_generate: steps exceed context");
     for (int i = 0; i < n_steps; ++i) {
         const int32_t* tok = (i == 0) ? first_token : tokens_out + (i - 1);
@@ -1120,6 +1255,7 @@ extern "C" int thk_decoder_generate(thk_decoder* d, const int32_t* first_token, 
 // (ProfSlot), followed by per-CTA producer stats [empty-wait cycles, total cycles, tiles, 0]
 extern "C" int thk_decoder_profile(thk_decoder* d, int enable, unsigned long long* host_out, int n) {
     THK_CHECK_ARG(d, "thk_decoder_profile: null argument");
+    THK_ENTER(d->ctx);
     if (enable && !d->d_prof) {
         const size_t nprof = (size_t)d->grid * kProfPhases * 8 + (size_t)d->grid * 4;
         THK_CUDA(cudaMalloc(&d->d_prof, nprof * sizeof(unsigned long long)));
@@ -1147,11 +1283,24 @@ extern "C" int thk_decoder_check(thk_decoder* d) {
     return check_status(d);
 }
 
-extern "C" int thk_decoder_exchange_info(thk_decoder*, void**, size_t*, void**, size_t*) {
-    thk_set_error("tensor-parallel exchange not built yet");
-    return THK_E_UNSUPPORTED;
+extern "C" int thk_decoder_exchange_info(thk_decoder* d, void** buf, size_t* buf_bytes, void** flags, size_t* flag_bytes) {
+    THK_CHECK_ARG(d && buf && buf_bytes, "thk_decoder_exchange_info: null argument");
+    THK_CHECK_ARG(d->p.tp_size > 1, "thk_decoder_exchange_info: decoder is not tensor parallel");
+    *buf = d->xchg; *buf_bytes = d->xchg_bytes;
+    if (flags) *flags = d->xchg + (size_t)2 * d->p.tp_size * d->p.n_embd * sizeof(float) + (size_t)2 * d->p.tp_size * sizeof(unsigned);
+    if (flag_bytes) *flag_bytes = (size_t)2 * d->p.tp_size * sizeof(unsigned);
+    return THK_OK;
 }
-extern "C" int thk_decoder_set_peers(thk_decoder*, void* const*, void* const*, int) {
-    thk_set_error("tensor-parallel exchange not built yet");
-    return THK_E_UNSUPPORTED;
+// peer_bufs[r]: rank r's exchange region as mapped into THIS process/device (cudaIpcOpenMemHandle or same-process
+// peer access); the entry for the local rank is ignored.  peer_flags is unused (flags live inside the region).
+extern "C" int thk_decoder_set_peers(thk_decoder* d, void* const* peer_bufs, void* const*, int n) {
+    THK_CHECK_ARG(d && peer_bufs, "thk_decoder_set_peers: null argument");
+    THK_CHECK_ARG(n == d->p.tp_size && n > 1, "thk_decoder_set_peers: expected %d peers, got %d", d->p.tp_size, n);
+    for (int r = 0; r < n; ++r) {
+        if (r == d->p.tp_rank) continue;
+        THK_CHECK_ARG(peer_bufs[r] != nullptr, "thk_decoder_set_peers: peer %d is null", r);
+        d->p.xchg[r] = (unsigned char*)peer_bufs[r];
+    }
+    d->peers_set = true;
+    return THK_OK;
 }

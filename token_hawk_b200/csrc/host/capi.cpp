@@ -34,6 +34,44 @@ void* capi_model_synthetic(void* ctx, int n_vocab, int n_embd, int n_mult, int n
     if (!m) { if (!*thk_last_error()) g_capi_err = "create_synthetic_llama failed"; return nullptr; }
     return new CapiModel{m, (thk_ctx*)ctx};
 }
+void* capi_model_synthetic_tp(void* ctx, int n_vocab, int n_embd, int n_mult, int n_head, int n_layer, int n_ctx, uint64_t seed, int tp_rank,
+                              int tp_size) {
+    g_capi_err.clear();
+    auto m = create_synthetic_llama((thk_ctx*)ctx, (thk_ctx*)ctx, n_vocab, n_embd, n_mult, n_head, n_layer, n_ctx, seed, tp_rank, tp_size);
+    if (!m) { if (!*thk_last_error()) g_capi_err = "create_synthetic_llama failed"; return nullptr; }
+    return new CapiModel{m, (thk_ctx*)ctx};
+}
+void* capi_model_load_tp(void* ctx, const char* path, int n_ctx, int tp_rank, int tp_size) {
+    g_capi_err.clear();
+    auto m = load_llama_file((thk_ctx*)ctx, (thk_ctx*)ctx, path, n_ctx, tp_rank, tp_size);
+    if (!m) { g_capi_err = std::string("load_llama_file failed: ") + path; return nullptr; }
+    return new CapiModel{m, (thk_ctx*)ctx};
+}
+// tensor-parallel wiring: this rank's exchange region, and the peers' regions as mapped here
+int capi_exchange_info(void* h, void** buf, uint64_t* bytes) {
+    auto& m = ((CapiModel*)h)->m;
+    size_t n = 0;
+    if (!m->decoder) return -1;
+    const int rc = thk_decoder_exchange_info(m->decoder, buf, &n, nullptr, nullptr);
+    *bytes = n;
+    return rc;
+}
+int capi_set_peers(void* h, void* const* bufs, int n) {
+    auto& m = ((CapiModel*)h)->m;
+    return m->decoder ? thk_decoder_set_peers(m->decoder, bufs, nullptr, n) : -1;
+}
+// th_eval_gpu in two halves (see th-llama.hpp)
+int capi_eval_launch(void* h, const int32_t* tokens, int n_tokens, int n_past) {
+    CapiModel* cm = (CapiModel*)h;
+    g_capi_err.clear();
+    return th_eval_gpu_launch(cm->ctx, cm->ctx, cm->m, tokens, n_tokens, n_past);
+}
+int capi_eval_finish(void* h, float* logits_out) {
+    CapiModel* cm = (CapiModel*)h;
+    const int tok = th_eval_gpu_finish(cm->ctx, cm->ctx, cm->m);
+    if (tok >= 0 && logits_out) memcpy(logits_out, cm->m->lastLogits.data(), sizeof(float) * cm->m->lastLogits.size());
+    return tok;
+}
 void* capi_model_load(void* ctx, const char* path, int n_ctx) {
     g_capi_err.clear();
     auto m = load_llama_file((thk_ctx*)ctx, (thk_ctx*)ctx, path, n_ctx);
@@ -49,9 +87,15 @@ int capi_model_dims(void* h, int32_t* out9) {
     memcpy(out9, v, sizeof v);
     return 0;
 }
+int capi_model_tp(void* h, int32_t* out2) {
+    auto& m = ((CapiModel*)h)->m;
+    out2[0] = m->tp_rank; out2[1] = m->tp_size;
+    return 0;
+}
 int capi_set_eval_path(void* h, int path) {
     auto& m = ((CapiModel*)h)->m;
     if (path == EvalPath_Fused && !m->decoder) { g_capi_err = "fused decoder unavailable"; return -1; }
+    if (path == EvalPath_OpGraph && m->tp_size > 1) { g_capi_err = "the op graph runs unsharded only"; return -1; }
     m->evalPath = (EvalPath)path;
     return 0;
 }
@@ -62,7 +106,7 @@ int capi_eval(void* h, const int32_t* tokens, int n_tokens, int n_past, float* l
     CapiModel* cm = (CapiModel*)h;
     g_capi_err.clear();
     const int tok = th_eval_gpu(cm->ctx, cm->ctx, cm->m, tokens, n_tokens, n_past);
-    if (tok >= 0 && logits_out) memcpy(logits_out, cm->m->lastLogits.data(), sizeof(float) * cm->m->n_vocab);
+    if (tok >= 0 && logits_out) memcpy(logits_out, cm->m->lastLogits.data(), sizeof(float) * cm->m->lastLogits.size());
     return tok;
 }
 int64_t capi_last_launches(void* h) { return ((CapiModel*)h)->m->gpuLaunches; }
@@ -86,7 +130,7 @@ int capi_generate_device(void* h, int first_token, int n_past, int n_steps, int3
     int rc = thk_upload(cm->ctx, m->d_token, 0, &first_token, sizeof(int32_t));
     if (!rc) rc = thk_decoder_generate(m->decoder, m->d_token, n_past, n_steps, (int32_t*)d_out, (float*)m->out.gpu);
     if (!rc) rc = thk_download(cm->ctx, out_host, d_out, 0, sizeof(int32_t) * (size_t)n_steps);
-    if (!rc && last_logits_host) rc = thk_download(cm->ctx, last_logits_host, m->out.gpu, 0, sizeof(float) * (size_t)m->n_vocab);
+    if (!rc && last_logits_host) rc = thk_download(cm->ctx, last_logits_host, m->out.gpu, 0, sizeof(float) * (size_t)(m->n_vocab / m->tp_size));
     if (!rc) rc = thk_decoder_check(m->decoder);
     thk_free(cm->ctx, d_out);
     m->gpuLaunches = n_steps;

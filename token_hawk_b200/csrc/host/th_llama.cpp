@@ -214,6 +214,13 @@ static bool eval_one_opgraph(WGPUDevice device, WGPUQueue queue, std::shared_ptr
 
 tk_llama_token th_eval_gpu(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens,
                            int n_tokens, int n_past) {
+    if (th_eval_gpu_launch(device, queue, m, tokens, n_tokens, n_past) != 0) return -1;
+    return th_eval_gpu_finish(device, queue, m);
+}
+
+// First half of th_eval_gpu: upload the token, enqueue the evaluation (no host wait).  Returns 0 on success.
+int th_eval_gpu_launch(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens, int n_tokens,
+                       int n_past) {
     if (!m || !tokens || n_tokens < 1) { fprintf(stderr, "th_eval_gpu: bad arguments\n"); return -1; }
     if (n_past < 0 || n_past + n_tokens > m->n_ctx) {
         fprintf(stderr, "th_eval_gpu: n_past %d + n_tokens %d exceeds the context (%d)\n", n_past, n_tokens, m->n_ctx);
@@ -237,14 +244,28 @@ tk_llama_token th_eval_gpu(WGPUDevice device, WGPUQueue queue, std::shared_ptr<L
             if (!eval_one_opgraph(device, queue, m, tok, n_past + i)) { fprintf(stderr, "th_eval_gpu: op graph failed\n"); return -1; }
         }
     }
-    // logits -> pinned host buffer (resultBuffer + map, th-llama.cpp:646-706), then sample on the host
-    if (thk_download(queue, m->pinnedLogits, m->out.gpu, 0, (size_t)m->n_vocab * sizeof(float))) {
+    m->gpuLaunches = (g_launch_count - launches0) + fused_launches;
+    return 0;
+}
+
+// Second half of th_eval_gpu: logits -> pinned host buffer (resultBuffer + map, th-llama.cpp:646-706), then
+// sample on the host.  Split out so that several tensor-parallel ranks driven by one thread can all be
+// launched before any of them is waited for.
+tk_llama_token th_eval_gpu_finish(WGPUDevice, WGPUQueue queue, std::shared_ptr<LlamaModel> m) {
+    const int64_t nlocal = m->n_vocab / m->tp_size;
+    if (thk_download(queue, m->pinnedLogits, m->out.gpu, 0, (size_t)nlocal * sizeof(float))) {
         fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error());
         return -1;
     }
     if (m->evalPath == EvalPath_Fused && thk_decoder_check(m->decoder)) { fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error()); return -1; }
-    m->gpuLaunches = (g_launch_count - launches0) + fused_launches;
-    m->lastLogits.assign(m->pinnedLogits, m->pinnedLogits + m->n_vocab);
+    m->lastLogits.assign(m->pinnedLogits, m->pinnedLogits + nlocal);
+    if (m->tp_size > 1) {
+        // each rank holds a vocabulary slice; the greedy id over the whole vocabulary was agreed on inside the kernel
+        int32_t tok = -1;
+        if (thk_download(queue, &tok, m->d_next, 0, sizeof tok)) { fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error()); return -1; }
+        if (m->samplerTemp > 0) { fprintf(stderr, "th_eval_gpu: tensor-parallel evaluation samples greedily\n"); return -1; }
+        return tok;
+    }
     return llama_sample_top_p_top_k(m, {}, 40, 0.95f, m->samplerTemp, 1.10f, m->lastLogits);
 }
 

@@ -91,11 +91,33 @@ bool load_weights(LlamaModel* m, WGPUDevice device, WGPUQueue queue, void* data,
     return true;
 }
 
-static TensorBuffer take(LlamaModel* m, const std::string& name, TensorType type, int64_t rows, int64_t cols, bool& ok) {
+// Shard kinds (Megatron-style tensor parallel): rows of the local heads / ff units / vocab
+// entries, or the matching columns for the matrices whose INPUT dimension is split (wo, w2).
+enum ShardKind { Shard_None, Shard_Rows, Shard_Cols };
+
+static TensorBuffer take(LlamaModel* m, const std::string& name, TensorType type, int64_t rows, int64_t cols, bool& ok,
+                         ShardKind shard = Shard_None) {
     auto it = m->loadedMapping.find(name);
     if (it == m->loadedMapping.end() || !it->second.gpu) { fprintf(stderr, "model is missing tensor %s\n", name.c_str()); ok = false; return {}; }
     TensorBuffer t = std::move(it->second);
     m->loadedMapping.erase(it);
+    const int64_t tp = m->tp_size, rk = m->tp_rank;
+    if (tp > 1 && shard != Shard_None && t.shape.r == rows * (shard == Shard_Rows ? tp : 1) && t.shape.c == cols * (shard == Shard_Cols ? tp : 1)) {
+        // the file (or a full synthetic tensor) holds the whole matrix: keep this rank's slice
+        const size_t es = get_TensorType_size(t.type);
+        TensorBuffer sl(TensorShape{0, 0, rows, cols}, t.type, m->device);
+        sl.name = t.name;
+        if (!sl.gpu) { ok = false; return {}; }
+        if (shard == Shard_Rows) {
+            thk_copy(m->device, sl.gpu, 0, t.gpu, (size_t)(rk * rows) * cols * es, (size_t)rows * cols * es);
+        } else {
+            const int64_t full = cols * tp;
+            for (int64_t r = 0; r < rows; ++r)
+                thk_copy(m->device, sl.gpu, (size_t)r * cols * es, t.gpu, ((size_t)r * full + rk * cols) * es, (size_t)cols * es);
+        }
+        thk_sync(m->device);
+        t = std::move(sl);
+    }
     if (t.type != type || t.shape.r != rows || t.shape.c != cols) {
         fprintf(stderr, "tensor %s: expected %s [%lld,%lld], file has %s %s\n", name.c_str(), get_TensorType_name(type).c_str(),
                 (long long)rows, (long long)cols, get_TensorType_name(t.type).c_str(), t.shape.to_string().c_str());
@@ -110,27 +132,30 @@ void post_load_init_model(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Ll
     m->rng = std::mt19937(780658349);                                       // :332
     m->n_ff = ((2 * (4 * m->n_embd) / 3 + m->n_mult - 1) / m->n_mult) * m->n_mult;   // :349
     const int64_t E = m->n_embd, H = m->n_head, D = E / H, F = m->n_ff, V = m->n_vocab;
+    const int64_t tp = m->tp_size > 0 ? m->tp_size : 1;
     bool ok = (E > 0 && H > 0 && E % H == 0 && m->n_layer > 0 && m->n_ctx > 0);
+    if (ok && (H % tp || F % tp || V % tp || m->tp_rank < 0 || m->tp_rank >= tp)) { fprintf(stderr, "post_load_init_model: tp_size %lld must divide n_head, n_ff and n_vocab\n", (long long)tp); ok = false; }
     if (!ok) { fprintf(stderr, "post_load_init_model: bad hyper-parameters\n"); m->loadFailed = true; return; }
+    const int64_t Eh = E / tp, Fh = F / tp, Vl = V / tp, Hl = H / tp;
 
     m->tok_embeddings = take(m.get(), "tok_embeddings.weight", TensorType_F16, V, E, ok);
     m->norm = take(m.get(), "norm.weight", TensorType_F32, 1, E, ok);
-    m->outputMat = take(m.get(), "output.weight", TensorType_F16, V, E, ok);
-    const TensorShape kvShape{0, m->n_ctx, H, D};          // [pos][head][dim], :335
-    const TensorShape kvShapeHpd{0, H, m->n_ctx, D};       // [head][pos][dim] for the fused kernel
+    m->outputMat = take(m.get(), "output.weight", TensorType_F16, Vl, E, ok, Shard_Rows);
+    const TensorShape kvShape{0, m->n_ctx, Hl, D};         // [pos][head][dim], :335
+    const TensorShape kvShapeHpd{0, Hl, m->n_ctx, D};      // [head][pos][dim] for the fused kernel
     for (int i = 0; i < m->n_layer && ok; ++i) {
         LlamaLayer l{};
         l.index = i;
         const std::string p = "layers." + std::to_string(i) + ".";
         l.attention_norm = take(m.get(), p + "attention_norm.weight", TensorType_F32, 1, E, ok);
-        l.wq = take(m.get(), p + "attention.wq.weight", TensorType_F16, E, E, ok);
-        l.wk = take(m.get(), p + "attention.wk.weight", TensorType_F16, E, E, ok);
-        l.wv = take(m.get(), p + "attention.wv.weight", TensorType_F16, E, E, ok);
-        l.wo = take(m.get(), p + "attention.wo.weight", TensorType_F16, E, E, ok);
+        l.wq = take(m.get(), p + "attention.wq.weight", TensorType_F16, Eh, E, ok, Shard_Rows);
+        l.wk = take(m.get(), p + "attention.wk.weight", TensorType_F16, Eh, E, ok, Shard_Rows);
+        l.wv = take(m.get(), p + "attention.wv.weight", TensorType_F16, Eh, E, ok, Shard_Rows);
+        l.wo = take(m.get(), p + "attention.wo.weight", TensorType_F16, E, Eh, ok, Shard_Cols);
         l.ffn_norm = take(m.get(), p + "ffn_norm.weight", TensorType_F32, 1, E, ok);
-        l.w1 = take(m.get(), p + "feed_forward.w1.weight", TensorType_F16, F, E, ok);
-        l.w2 = take(m.get(), p + "feed_forward.w2.weight", TensorType_F16, E, F, ok);
-        l.w3 = take(m.get(), p + "feed_forward.w3.weight", TensorType_F16, F, E, ok);
+        l.w1 = take(m.get(), p + "feed_forward.w1.weight", TensorType_F16, Fh, E, ok, Shard_Rows);
+        l.w2 = take(m.get(), p + "feed_forward.w2.weight", TensorType_F16, E, Fh, ok, Shard_Cols);
+        l.w3 = take(m.get(), p + "feed_forward.w3.weight", TensorType_F16, Fh, E, ok, Shard_Rows);
         l.key_cache = TensorBuffer(kvShape, TensorType_F32, device);
         l.value_cache = TensorBuffer(kvShape, TensorType_F32, device);
         l.key_cache_hpd = TensorBuffer(kvShapeHpd, TensorType_F32, device);
@@ -155,8 +180,8 @@ void post_load_init_model(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Ll
     }
     m->ffWorking[0] = TensorBuffer(TensorShape{0, 0, m->n_batch, F}, TensorType_F32, device);   // :351-352
     m->ffWorking[1] = TensorBuffer(TensorShape{0, 0, m->n_batch, F}, TensorType_F32, device);
-    m->out = TensorBuffer(TensorShape{0, 0, 1, V}, TensorType_F32, device);                     // :360
-    m->outScratch = TensorBuffer(TensorShape{0, 0, 1, V}, TensorType_F32, device);
+    m->out = TensorBuffer(TensorShape{0, 0, 1, Vl}, TensorType_F32, device);                    // :360
+    m->outScratch = TensorBuffer(TensorShape{0, 0, 1, Vl}, TensorType_F32, device);
     void* p = nullptr;
     if (thk_host_alloc(device, (size_t)V * sizeof(float), &p) == THK_OK) m->pinnedLogits = (float*)p;     // resultBuffer, :363
     LlamaNetworkUniforms zero{};
@@ -168,12 +193,12 @@ void post_load_init_model(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Ll
     m->d_token = (int32_t*)t0; m->d_next = (int32_t*)t1;
     if (!m->pinnedLogits || !m->networkUniforms || !m->d_token || !m->d_next || !m->out.gpu) { m->loadFailed = true; return; }
 
-    build_pipelines_llama(device, queue, m);                                                    // :434
+    if (tp == 1) build_pipelines_llama(device, queue, m);                                       // :434 (op graph: unsharded only)
 
     // fused decoder over the same weights
     thk_llama_dims dims{};
     dims.n_vocab = m->n_vocab; dims.n_embd = m->n_embd; dims.n_head = m->n_head; dims.n_layer = m->n_layer;
-    dims.n_ff = m->n_ff; dims.n_ctx = m->n_ctx; dims.tp_rank = 0; dims.tp_size = 1;
+    dims.n_ff = m->n_ff; dims.n_ctx = m->n_ctx; dims.tp_rank = m->tp_rank; dims.tp_size = (int32_t)tp;
     std::vector<thk_llama_layer> L(m->n_layer);
     for (int i = 0; i < m->n_layer; ++i) {
         const LlamaLayer& l = m->layers[i];
@@ -188,18 +213,22 @@ void post_load_init_model(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Ll
         fprintf(stderr, "post_load_init_model: fused decoder unavailable (%s); op graph only\n", thk_last_error());
         m->decoder = nullptr;
         m->evalPath = EvalPath_OpGraph;
+        if (tp > 1) { m->loadFailed = true; return; }
     }
     thk_sync(queue);
 }
 
 // th-llama-loader.cpp:485-635
-std::shared_ptr<LlamaModel> load_llama_file(WGPUDevice device, WGPUQueue queue, const std::string& filename, int32_t n_ctx) {
+std::shared_ptr<LlamaModel> load_llama_file(WGPUDevice device, WGPUQueue queue, const std::string& filename, int32_t n_ctx, int32_t tp_rank,
+                                            int32_t tp_size) {
     std::ifstream fin(filename, std::ios::binary | std::ios::ate);
     if (!fin) { fprintf(stderr, "Unable to open file: %s\n", filename.c_str()); return {}; }
     const int64_t fileSize = (int64_t)fin.tellg();
     fin.seekg(0, std::ios::beg);
     auto m = std::make_shared<LlamaModel>();
     m->n_ctx = n_ctx;
+    m->tp_rank = tp_rank; m->tp_size = tp_size > 0 ? tp_size : 1;
+    m->device = device;
 
     // header + vocab: read a bounded prefix, parse with load_header, then find where it ended
     {
@@ -260,17 +289,28 @@ static const char* kLayerTensorNames[9] = {"attention_norm.weight", "attention.w
                                            "feed_forward.w3.weight"};
 
 std::shared_ptr<LlamaModel> create_synthetic_llama(WGPUDevice device, WGPUQueue queue, int32_t n_vocab, int32_t n_embd, int32_t n_mult,
-                                                   int32_t n_head, int32_t n_layer, int32_t n_ctx, uint64_t seed) {
+                                                   int32_t n_head, int32_t n_layer, int32_t n_ctx, uint64_t seed, int32_t tp_rank,
+                                                   int32_t tp_size) {
     auto m = std::make_shared<LlamaModel>();
+    m->tp_rank = tp_rank; m->tp_size = tp_size > 0 ? tp_size : 1;
+    m->device = device;
+    if (n_head % m->tp_size || n_vocab % m->tp_size) { fprintf(stderr, "create_synthetic_llama: tp_size must divide n_head and n_vocab\n"); return {}; }
     m->n_vocab = n_vocab; m->n_embd = n_embd; m->n_mult = n_mult; m->n_head = n_head; m->n_layer = n_layer;
     m->n_rot = n_head ? n_embd / n_head : 0; m->n_ctx = n_ctx; m->f16 = 1;
     const int64_t E = n_embd, V = n_vocab;
     const int64_t F = ((2 * (4 * E) / 3 + n_mult - 1) / n_mult) * n_mult;
     bool ok = true;
-    auto mat = [&](const std::string& name, uint64_t id, int64_t R, int64_t C) {
-        TensorBuffer t(TensorShape{0, 0, R, C}, TensorType_F16, device);
+    const int64_t tp = m->tp_size, rk = m->tp_rank;
+    if (F % tp) { fprintf(stderr, "create_synthetic_llama: tp_size must divide n_ff\n"); return {}; }
+    // shard: 0 none, 1 rows, 2 cols -- each rank generates only its slice of the full [R, C] tensor
+    auto mat = [&](const std::string& name, uint64_t id, int64_t R, int64_t C, int shard = 0) {
+        const int64_t r = shard == 1 ? R / tp : R, c = shard == 2 ? C / tp : C;
+        TensorBuffer t(TensorShape{0, 0, r, c}, TensorType_F16, device);
         t.name = name;
-        if (!t.gpu || thk_fill_f16(device, (uint16_t*)t.gpu, seed, id, R, C, 0, 0, C)) { fprintf(stderr, "synthetic %s: %s\n", name.c_str(), thk_last_error()); ok = false; }
+        if (!t.gpu || thk_fill_f16(device, (uint16_t*)t.gpu, seed, id, r, c, shard == 1 ? rk * r : 0, shard == 2 ? rk * c : 0, C)) {
+            fprintf(stderr, "synthetic %s: %s\n", name.c_str(), thk_last_error());
+            ok = false;
+        }
         m->loadedMapping[name] = std::move(t);
     };
     auto gain = [&](const std::string& name, uint64_t id) {
@@ -281,15 +321,16 @@ std::shared_ptr<LlamaModel> create_synthetic_llama(WGPUDevice device, WGPUQueue 
     };
     mat("tok_embeddings.weight", 0, V, E);
     gain("norm.weight", 1);
-    mat("output.weight", 2, V, E);
+    mat("output.weight", 2, V, E, 1);
     for (int l = 0; l < n_layer && ok; ++l)
         for (int k = 0; k < 9; ++k) {
             const std::string name = "layers." + std::to_string(l) + "." + kLayerTensorNames[k];
             const uint64_t id = 3 + 9ull * l + k;
             if (k == 0 || k == 5) gain(name, id);
-            else if (k == 6 || k == 8) mat(name, id, F, E);
-            else if (k == 7) mat(name, id, E, F);
-            else mat(name, id, E, E);
+            else if (k == 6 || k == 8) mat(name, id, F, E, 1);
+            else if (k == 7) mat(name, id, E, F, 2);
+            else if (k == 4) mat(name, id, E, E, 2);
+            else mat(name, id, E, E, 1);
         }
     if (!ok) return {};
     thk_sync(queue);
@@ -301,15 +342,15 @@ std::shared_ptr<LlamaModel> create_synthetic_llama(WGPUDevice device, WGPUQueue 
 
 bool fill_kv_synthetic(std::shared_ptr<LlamaModel> m, uint64_t seed, int n_positions) {
     if (!m || n_positions < 1 || n_positions > m->n_ctx) return false;
-    const int64_t H = m->n_head, D = m->n_embd / m->n_head;
+    const int64_t H = m->n_head, D = m->n_embd / m->n_head, Hl = H / m->tp_size, h0 = m->tp_rank * Hl;
     for (int l = 0; l < m->n_layer; ++l) {
         LlamaLayer& L = m->layers[l];
-        // fused layout [head][pos][dim]
-        if (thk_fill_kv(m->device, (float*)L.key_cache_hpd.gpu, seed, 1000 + 2ull * l, n_positions, m->n_ctx, H, 0, H, D)) return false;
-        if (thk_fill_kv(m->device, (float*)L.value_cache_hpd.gpu, seed, 1001 + 2ull * l, n_positions, m->n_ctx, H, 0, H, D)) return false;
+        // fused layout [head][pos][dim] (local heads only under tensor parallelism)
+        if (thk_fill_kv(m->device, (float*)L.key_cache_hpd.gpu, seed, 1000 + 2ull * l, n_positions, m->n_ctx, H, h0, Hl, D)) return false;
+        if (thk_fill_kv(m->device, (float*)L.value_cache_hpd.gpu, seed, 1001 + 2ull * l, n_positions, m->n_ctx, H, h0, Hl, D)) return false;
         // reference layout [pos][head][dim] = transpose of the above (zy on [H][n_ctx][D])
-        if (thk_transpose(m->device, (const float*)L.key_cache_hpd.gpu, (float*)L.key_cache.gpu, H, m->n_ctx, D, 1, nullptr)) return false;
-        if (thk_transpose(m->device, (const float*)L.value_cache_hpd.gpu, (float*)L.value_cache.gpu, H, m->n_ctx, D, 1, nullptr)) return false;
+        if (thk_transpose(m->device, (const float*)L.key_cache_hpd.gpu, (float*)L.key_cache.gpu, Hl, m->n_ctx, D, 1, nullptr)) return false;
+        if (thk_transpose(m->device, (const float*)L.value_cache_hpd.gpu, (float*)L.value_cache.gpu, Hl, m->n_ctx, D, 1, nullptr)) return false;
     }
     return thk_sync(m->device) == THK_OK;
 }

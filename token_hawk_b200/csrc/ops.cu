@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) matvec_kernel(const float* __restrict__ a
 
 extern "C" int thk_vector_mat_mul_trans(thk_ctx* ctx, const float* a, size_t a_offset_bytes, const void* B,
                                         float* c, int64_t R, int64_t C, int64_t batch, int b_is_f16) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && a && B && c, "thk_vector_mat_mul_trans: null argument");
     THK_CHECK_ARG(R > 0 && C > 0, "thk_vector_mat_mul_trans: R=%lld C=%lld", (long long)R, (long long)C);
     THK_CHECK_ARG(a_offset_bytes % 16 == 0, "thk_vector_mat_mul_trans: aOffset %zu not 16-byte aligned", a_offset_bytes);
@@ -95,6 +96,7 @@ static inline unsigned ew_blocks(const thk_ctx* ctx, int64_t n) {
 }
 
 extern "C" int thk_vector_reduce(thk_ctx* ctx, float* a, const float* b, int64_t n) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && a && b && n > 0, "thk_vector_reduce: bad argument");
     add_inplace_kernel<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>(a, b, n);
     THK_LAUNCH_CHECK();
@@ -104,6 +106,7 @@ extern "C" int thk_vector_reduce(thk_ctx* ctx, float* a, const float* b, int64_t
 extern "C" int thk_vector_multi_mat_mul_split_trans(thk_ctx* ctx, const float* a, size_t a_offset_bytes,
                                                     const void* const* B_splits, int nsplit, float* c,
                                                     float* scratch, int64_t R, int64_t C_total, int b_is_f16) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && a && B_splits && c, "thk_vector_multi_mat_mul_split_trans: null argument");
     THK_CHECK_ARG(nsplit >= 1 && C_total % nsplit == 0, "split count %d does not divide C=%lld", nsplit, (long long)C_total);
     THK_CHECK_ARG(nsplit == 1 || scratch, "thk_vector_multi_mat_mul_split_trans: scratch needed for %d splits", nsplit);
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(256) rms_norm_kernel(float* __restrict__ x, in
     for (int64_t i = threadIdx.x; i < N; i += 256) row[i] = row[i] * inv;
 }
 extern "C" int thk_rms_norm(thk_ctx* ctx, float* x, int64_t rows, int64_t N) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && x && rows > 0 && N > 0, "thk_rms_norm: bad argument");
     rms_norm_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(x, N);
     THK_LAUNCH_CHECK();
@@ -150,6 +154,7 @@ __global__ void row_mul_kernel(float* x, const float* g, int64_t total, int64_t 
         x[i] = x[i] * g[i % N];
 }
 extern "C" int thk_row_element_multiply(thk_ctx* ctx, float* x, const float* gain, int64_t rows, int64_t N) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && x && gain && rows > 0 && N > 0, "thk_row_element_multiply: bad argument");
     row_mul_kernel<<<ew_blocks(ctx, rows * N), 256, 0, ctx->stream>>>(x, gain, rows * N, N);
     THK_LAUNCH_CHECK();
@@ -179,6 +184,7 @@ __global__ void rope_kernel(float* x, int64_t n_tokens, int64_t n_head, int64_t 
 }
 extern "C" int thk_rope(thk_ctx* ctx, float* x, int64_t n_tokens, int64_t n_head, int64_t head_dim,
                         const thk_network_uniforms* uniforms) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && x && uniforms, "thk_rope: null argument");
     THK_CHECK_ARG(n_tokens > 0 && n_head > 0 && head_dim > 0 && head_dim % 2 == 0, "thk_rope: bad shape");
     rope_kernel<<<ew_blocks(ctx, n_tokens * n_head * head_dim / 2), 256, 0, ctx->stream>>>(x, n_tokens, n_head, head_dim, uniforms);
@@ -201,6 +207,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 }
 extern "C" int thk_transpose(thk_ctx* ctx, const float* in, float* out, int64_t B, int64_t M, int64_t N, int zy,
                              const thk_dims_uniforms* uniforms) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && in && out, "thk_transpose: null argument");
     THK_CHECK_ARG(in != out, "thk_transpose: in-place transpose is not supported");
     if (B <= 0) B = 1;
@@ -255,6 +262,7 @@ __global__ void __launch_bounds__(128) mat_mul_nn_kernel(const float* __restrict
 }
 extern "C" int thk_mat_mul(thk_ctx* ctx, const float* A, const void* B, float* C, int64_t batch, int64_t M, int64_t K,
                            int64_t N, int transposeB, int b_is_f16, const thk_dims_uniforms* uniforms) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && A && B && C, "thk_mat_mul: null argument");
     if (batch <= 0) batch = 1;
     THK_CHECK_ARG(M > 0 && K > 0 && N > 0, "thk_mat_mul: one of the dimensions is zero");
@@ -313,9 +321,11 @@ static int softmax_launch(thk_ctx* ctx, float* a, int64_t batch, int64_t M, int6
     return THK_OK;
 }
 extern "C" int thk_row_softmax(thk_ctx* ctx, float* a, int64_t batch, int64_t M, int64_t N, const thk_dims_uniforms* u) {
+    THK_ENTER(ctx);
     return softmax_launch(ctx, a, batch, M, N, 0, u, "thk_row_softmax");
 }
 extern "C" int thk_masked_softmax(thk_ctx* ctx, float* a, int64_t batch, int64_t M, int64_t N, const thk_dims_uniforms* u) {
+    THK_ENTER(ctx);
     return softmax_launch(ctx, a, batch, M, N, 1, u, "thk_masked_softmax");
 }
 
@@ -340,24 +350,28 @@ __global__ void f16_f32_kernel(float* out, const uint16_t* in, int64_t n) {
         out[i] = __half2float(__ushort_as_half(in[i]));
 }
 extern "C" int thk_addition(thk_ctx* ctx, const float* a, const float* b, float* c, int64_t n) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && a && b && c && n > 0, "thk_addition: bad argument");
     add_kernel<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>(a, b, c, n);
     THK_LAUNCH_CHECK();
     return THK_OK;
 }
 extern "C" int thk_silu(thk_ctx* ctx, float* a, int64_t n) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && a && n > 0, "thk_silu: bad argument");
     silu_kernel<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>(a, n);
     THK_LAUNCH_CHECK();
     return THK_OK;
 }
 extern "C" int thk_element_mult_in_place(thk_ctx* ctx, float* a, const float* b, int64_t n) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && a && b && n > 0, "thk_element_mult_in_place: bad argument");
     mul_kernel<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>(a, b, n);
     THK_LAUNCH_CHECK();
     return THK_OK;
 }
 extern "C" int thk_f16_f32_conversion(thk_ctx* ctx, float* out, size_t out_off, const uint16_t* in, size_t in_off, int64_t n) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && out && in && n > 0, "thk_f16_f32_conversion: bad argument");
     THK_CHECK_ARG(out_off % 4 == 0 && in_off % 2 == 0, "thk_f16_f32_conversion: misaligned offsets");
     f16_f32_kernel<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>((float*)((char*)out + out_off), (const uint16_t*)((const char*)in + in_off), n);
@@ -395,12 +409,14 @@ __global__ void fill_kv_kernel(float* dst, uint64_t seed, uint64_t tid, int64_t 
 }
 extern "C" int thk_fill_f16(thk_ctx* ctx, uint16_t* dst, uint64_t seed, uint64_t tid, int64_t rows, int64_t cols,
                             int64_t row0, int64_t col0, int64_t full_cols) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && dst && rows > 0 && cols > 0, "thk_fill_f16: bad argument");
     fill_f16_kernel<<<ew_blocks(ctx, rows * cols), 256, 0, ctx->stream>>>(dst, seed, tid, rows, cols, row0, col0, full_cols);
     THK_LAUNCH_CHECK();
     return THK_OK;
 }
 extern "C" int thk_fill_gain(thk_ctx* ctx, float* dst, uint64_t seed, uint64_t tid, int64_t n) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && dst && n > 0, "thk_fill_gain: bad argument");
     fill_gain_kernel<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>(dst, seed, tid, n);
     THK_LAUNCH_CHECK();
@@ -408,6 +424,7 @@ extern "C" int thk_fill_gain(thk_ctx* ctx, float* dst, uint64_t seed, uint64_t t
 }
 extern "C" int thk_fill_kv(thk_ctx* ctx, float* dst, uint64_t seed, uint64_t tid, int64_t n_pos, int64_t n_ctx,
                            int64_t H, int64_t head0, int64_t Hl, int64_t D) {
+    THK_ENTER(ctx);
     THK_CHECK_ARG(ctx && dst && n_pos > 0 && n_pos <= n_ctx, "thk_fill_kv: bad argument");
     fill_kv_kernel<<<ew_blocks(ctx, Hl * n_pos * D), 256, 0, ctx->stream>>>(dst, seed, tid, n_pos, n_ctx, H, head0, Hl, D);
     THK_LAUNCH_CHECK();

@@ -55,7 +55,7 @@ struct LlamaVocab {                  // th-llama.hpp:87-98
 struct LlamaModel {                  // th-llama.hpp:100-177
     std::mt19937 rng{};
     int32_t n_vocab = 32000, n_ctx = 512, n_embd = 4096, n_mult = 256, n_head = 32, n_layer = 32, n_rot = 64;
-    int32_t n_batch = 8;
+    int32_t n_batch = 128;           // tokens per batched-prompt pass (reference: 8, th-llama.cpp:14)
     int32_t f16 = 1;
     int32_t n_ff = 11008;            // derived at load (th-llama-loader.cpp:349); no 11008 assert here
 
@@ -101,6 +101,7 @@ struct LlamaModel {                  // th-llama.hpp:100-177
     float* pinnedLogits = nullptr;
     std::vector<float> lastLogits;
     int64_t gpuLaunches = 0;         // kernels launched by the last th_eval_gpu call
+    bool batchPrefill = true;        // n_tokens > 1: one batched pass (tensor-core matmuls) instead of n single-token steps
     int32_t tp_rank = 0, tp_size = 1; // tensor parallel: this model holds rank tp_rank's shard (fused path only)
 
     ~LlamaModel();

@@ -121,6 +121,10 @@ int thk_element_mult_in_place(thk_ctx* ctx, float* a, const float* b, int64_t n)
 int thk_f16_f32_conversion(thk_ctx* ctx, float* out, size_t out_offset_bytes, const uint16_t* in,
                            size_t in_offset_bytes, int64_t n);
 
+/* KV rows [pos0, pos0+npos) from the op graph's [pos][head][dim] cache into the fused decoder's
+ * [head][n_ctx][dim] cache (hand-over from batched prefill to single-token decode) */
+int thk_kv_to_hpd(thk_ctx* ctx, const float* src_phd, float* dst_hpd, int64_t pos0, int64_t npos, int64_t n_ctx, int64_t H, int64_t D);
+
 /* ---- synthetic tensors (no reference analogue): same counter PRNG as the oracle ---- */
 int thk_fill_f16(thk_ctx* ctx, uint16_t* dst, uint64_t seed, uint64_t tensor_id, int64_t rows, int64_t cols,
                  int64_t row0, int64_t col0, int64_t full_cols);
@@ -192,6 +196,8 @@ int thk_decoder_set_peers(thk_decoder* dec, void* const* peer_bufs, void* const*
  * 404, 429-430, 444). tcgen05 + TMEM + TMA; X is split into f16 hi + lo terms so the result keeps
  * f32-activation accuracy. */
 int thk_gemm_f16_tc(thk_ctx* ctx, const float* X, const uint16_t* W, float* Y, int64_t M, int64_t N, int64_t K);
+/* blocks on the stream; THK_E_TIMEOUT if a GEMM launch hit its in-kernel watchdog */
+int thk_gemm_check(thk_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -93,13 +93,65 @@ def test_greedy_ids_bit_exact_full_context(th, dev, oracle):
 
 
 def test_batch_eval_is_sequential_eval(th, dev, oracle):
+    """n_tokens > 1: one batched pass (tensor-core matmuls, causal mask with n_past) == n single-token steps,
+    and the fused decoder continues from the KV rows the batched pass wrote."""
     cfg = oracle.TINY
     g, o = make_pair(th, dev, oracle, cfg)
-    toks = [3, 9, 27, 81, 243, 11, 33, 99]
-    tok, logits = g.eval(toks, 0)
-    ref = o.eval(toks, 0)
-    assert rel(logits, ref) < 2e-5 and tok == oracle.greedy(ref)
+    toks = [3, 9, 27, 81, 243, 11, 33, 99, 5, 6, 7]
+    tok, logits = g.eval(toks[:8], 0)                       # batched prefill at n_past = 0
+    ref = o.eval(toks[:8], 0)
+    assert rel(logits, ref) < 5e-5 and tok == oracle.greedy(ref)
+    tok, logits = g.eval(toks[8:], 8)                       # second batch on top of a non-empty cache
+    ref = o.eval(toks[8:], 8)
+    assert rel(logits, ref) < 5e-5 and tok == oracle.greedy(ref)
+    n = len(toks)
+    for i in range(6):                                      # decode continues on the fused path
+        nxt = oracle.greedy(ref)
+        tok2, logits = g.eval([nxt], n + i)
+        ref = o.eval([nxt], n + i)
+        assert rel(logits, ref) < 5e-5 and tok2 == oracle.greedy(ref)
+    # the sequential fallback gives the same answer
+    g2, _ = make_pair(th, dev, oracle, cfg)
+    g2.set_batch_prefill(False)
+    t_seq, l_seq = g2.eval(toks[:8], 0)
+    o2 = oracle.Model.synthetic(cfg)
+    assert rel(l_seq, o2.eval(toks[:8], 0)) < 2e-5
+    g.close(); g2.close()
+
+
+def test_prefill_128_tokens(th, dev, oracle):
+    """BASELINE configs[2]: a 128-token prompt in ONE batched pass on the tensor-core path, then decode.
+    (a) small model vs the oracle's 128 sequential steps; (b) 7B tensor shapes (2 layers): batched pass vs
+    128 sequential fused steps on the GPU (the sequential path is checked against the oracle elsewhere --
+    running the oracle 128 times at 7B width would take minutes of CPU on the GPU box)."""
+    r = np.random.default_rng(3)
+    cfg = oracle.Config(n_vocab=512, n_embd=512, n_mult=256, n_head=8, n_layer=2, n_ctx=160)
+    g, o = make_pair(th, dev, oracle, cfg)
+    prompt = r.integers(0, cfg.n_vocab, 128).tolist()
+    tok, logits = g.eval(prompt, 0)
+    ref = o.eval(prompt, 0)
+    assert rel(logits, ref) < 1e-4 and tok == oracle.greedy(ref), rel(logits, ref)
+    for i in range(3):
+        nxt = oracle.greedy(ref)
+        tok, logits = g.eval([nxt], 128 + i)
+        ref = o.eval([nxt], 128 + i)
+        assert rel(logits, ref) < 1e-4 and tok == oracle.greedy(ref)
     g.close()
+
+    cfg = oracle.Config(n_layer=2, n_ctx=160)
+    a = th.LlamaModel.synthetic(dev, cfg.n_vocab, cfg.n_embd, cfg.n_mult, cfg.n_head, cfg.n_layer, cfg.n_ctx)
+    b = th.LlamaModel.synthetic(dev, cfg.n_vocab, cfg.n_embd, cfg.n_mult, cfg.n_head, cfg.n_layer, cfg.n_ctx)
+    b.set_batch_prefill(False)
+    prompt = r.integers(0, cfg.n_vocab, 128).tolist()
+    ta, la = a.eval(prompt, 0)
+    tb, lb = b.eval(prompt, 0)
+    assert rel(la, lb) < 1e-4 and ta == tb, rel(la, lb)
+    assert a.last_launches > 100 and b.last_launches == 128
+    for i in range(3):
+        ta, la = a.eval([ta], 128 + i)
+        tb, lb = b.eval([tb], 128 + i)
+        assert rel(la, lb) < 1e-4 and ta == tb
+    a.close(); b.close()
 
 
 def test_error_behaviour(th, dev, oracle):

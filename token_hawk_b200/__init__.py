@@ -76,6 +76,7 @@ def kernels() -> C.CDLL:
             "thk_silu": [vp, vp, i64],
             "thk_element_mult_in_place": [vp, vp, vp, i64],
             "thk_f16_f32_conversion": [vp, vp, C.c_size_t, vp, C.c_size_t, i64],
+            "thk_kv_to_hpd": [vp, vp, vp, i64, i64, i64, i64, i64],
             "thk_fill_f16": [vp, vp, u64, u64, i64, i64, i64, i64, i64],
             "thk_fill_gain": [vp, vp, u64, u64, i64],
             "thk_fill_kv": [vp, vp, u64, u64, i64, i64, i64, i64, i64, i64],
@@ -90,6 +91,7 @@ def kernels() -> C.CDLL:
             "thk_decoder_exchange_info": [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t)],
             "thk_decoder_set_peers": [vp, C.POINTER(vp), C.POINTER(vp), C.c_int],
             "thk_gemm_f16_tc": [vp, vp, vp, vp, i64, i64, i64],
+            "thk_gemm_check": [vp],
             "thk_ipc_export": [vp, vp, C.POINTER(C.c_ubyte)],
             "thk_ipc_import": [vp, C.POINTER(C.c_ubyte), C.POINTER(vp)],
             "thk_ipc_close": [vp, vp],
@@ -133,6 +135,7 @@ def host() -> C.CDLL:
         H.capi_model_dims.argtypes = [vp, i32p]
         H.capi_set_eval_path.argtypes = [vp, C.c_int]
         H.capi_reset.argtypes = [vp]
+        H.capi_set_batch_prefill.argtypes = [vp, C.c_int]
         H.capi_eval.argtypes = [vp, i32p, C.c_int, C.c_int, f32p]
         H.capi_last_launches.restype = i64
         H.capi_last_launches.argtypes = [vp]
@@ -318,6 +321,10 @@ class LlamaModel:
 
     def reset(self):
         host().capi_reset(self.h)
+
+    def set_batch_prefill(self, on: bool):
+        """n_tokens > 1: one batched pass on the tensor cores (default) or n single-token steps."""
+        host().capi_set_batch_prefill(self.h, int(on))
 
     def generate_device(self, first_token: int, n_past: int, n_steps: int, want_logits=False):
         out = np.empty(n_steps, np.int32)

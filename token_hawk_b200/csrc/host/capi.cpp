@@ -100,6 +100,7 @@ int capi_set_eval_path(void* h, int path) {
     return 0;
 }
 void capi_reset(void* h) { ((CapiModel*)h)->m->n_past = 0; }
+void capi_set_batch_prefill(void* h, int on) { ((CapiModel*)h)->m->batchPrefill = on != 0; }
 
 // th_eval_gpu: tokens (host), returns sampled (greedy) token or -1; logits_out (host, n_vocab) optional
 int capi_eval(void* h, const int32_t* tokens, int n_tokens, int n_past, float* logits_out) {

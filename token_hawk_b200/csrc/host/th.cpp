@@ -207,7 +207,10 @@ CommandBuffer cmdbuf_mat_mul(WGPUDevice device, WGPUCommandEncoder encoder, WGPU
     const float* a = (const float*)A.gpu; const void* b = B.gpu; float* c = (float*)C.gpu;
     const int64_t batch = dim1(A.shape.b), M = A.shape.r, K = A.shape.c, N = B.shape.c;
     const int f16 = B.type == TensorType_F16;
+    // batched-prompt weight matmul (th-llama.cpp:308-310,404,429-430,444): dense contraction -> tensor cores
+    const bool tc = f16 && transposeB && batch == 1 && !useUniforms && M >= 8 && N % 32 == 0 && K % 64 == 0;
     return emit(encoder, pass, "cmdbuf_mat_mul", [=]() {
+        if (tc) return thk_gemm_f16_tc(device, a, (const uint16_t*)b, c, M, N, K);
         return thk_mat_mul(device, a, b, c, batch, M, K, N, transposeB, f16, (const thk_dims_uniforms*)uniforms); });
 }
 

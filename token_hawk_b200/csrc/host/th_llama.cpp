@@ -72,13 +72,85 @@ void build_final_compute_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, s
     x.shape = keep;
 }
 
+// th-llama.cpp:270-452, n_tokens > 1 branch (the reference's `pb` path, generalised): any batch size up to
+// n_batch, a causal mask that honours n_past (the reference's masked softmax ignores it), and the
+// weight matmuls on the tensor cores (cmdbuf_mat_mul -> thk_gemm_f16_tc).  Pipelines are not cached here:
+// the shapes change with the batch size.
+static void build_layer_cmdbuf_batch(WGPUDevice device, WGPUCommandEncoder encoder, std::shared_ptr<LlamaModel> m, LlamaLayer& l,
+                                     int n_tokens, int n_past) {
+    if (!encoder) return;                         // nothing to pre-build
+    TensorBuffer& queryBuf = m->inp[1];
+    TensorBuffer& keyBuf = m->inp[2];
+    TensorBuffer& valueBuf = m->inp[3];
+    TensorBuffer& queryTranspose = m->inp[4];
+    const int n_embd = m->n_embd, n_head = m->n_head, hd = n_embd / n_head, T = n_tokens, N = n_past + n_tokens;
+    const TensorShape rows{0, 0, T, n_embd};
+    for (TensorBuffer* t : {&m->inp[0], &queryBuf, &keyBuf, &valueBuf, &queryTranspose, &m->inp[6]}) t->shape = rows;
+
+    cmdbuf_rms_norm(device, encoder, nullptr, nullptr, m->inp[0]);
+    cmdbuf_row_element_multiply(device, encoder, nullptr, nullptr, m->inp[0], l.attention_norm);
+    cmdbuf_mat_mul(device, encoder, nullptr, nullptr, m->inp[0], l.wq, queryBuf, 1);             // :308-310
+    cmdbuf_mat_mul(device, encoder, nullptr, nullptr, m->inp[0], l.wk, keyBuf, 1);
+    cmdbuf_mat_mul(device, encoder, nullptr, nullptr, m->inp[0], l.wv, valueBuf, 1);
+
+    queryBuf.shape = TensorShape{0, T, n_head, hd};
+    keyBuf.shape = TensorShape{0, T, n_head, hd};
+    cmdbuf_RoPE(device, encoder, nullptr, nullptr, queryBuf, m->networkUniforms);
+    cmdbuf_RoPE(device, encoder, nullptr, nullptr, keyBuf, m->networkUniforms);
+    const size_t off = (size_t)n_past * n_embd * sizeof(float), bytes = (size_t)T * n_embd * sizeof(float);
+    thk_copy(device, l.key_cache.gpu, off, keyBuf.gpu, 0, bytes);                                // :337-338
+    thk_copy(device, l.value_cache.gpu, off, valueBuf.gpu, 0, bytes);
+
+    l.key_cache.shape.b = N;
+    l.value_cache.shape.b = N;
+    m->working_key_cache.shape = TensorShape{0, n_head, N, hd};
+    m->working_val_cache.shape = TensorShape{0, n_head, N, hd};
+    queryTranspose.shape = TensorShape{0, n_head, T, hd};
+    cmdbuf_transpose(device, encoder, nullptr, nullptr, l.key_cache, m->working_key_cache, true, m->dimsUniforms[0]);
+    cmdbuf_transpose(device, encoder, nullptr, nullptr, l.value_cache, m->working_val_cache, true, m->dimsUniforms[0]);
+    cmdbuf_transpose(device, encoder, nullptr, nullptr, queryBuf, queryTranspose, true, m->dimsUniforms[1]);
+
+    std::swap(m->working_key_cache.shape.r, m->working_key_cache.shape.c);                       // logical [H, D, N] for A.c == B.r
+    m->inp[5].shape = TensorShape{0, n_head, T, N};
+    cmdbuf_mat_mul(device, encoder, nullptr, nullptr, queryTranspose, m->working_key_cache, m->inp[5], 1, m->dimsUniforms[2]);
+    cmdbuf_masked_softmax(device, encoder, nullptr, nullptr, m->inp[5], m->dimsUniforms[3]);     // causal, row i sees <= n_past + i
+    keyBuf.shape = TensorShape{0, n_head, T, hd};
+    cmdbuf_mat_mul(device, encoder, nullptr, nullptr, m->inp[5], m->working_val_cache, keyBuf, 0, m->dimsUniforms[4]);
+    valueBuf.shape = TensorShape{0, T, n_head, hd};
+    cmdbuf_transpose(device, encoder, nullptr, nullptr, keyBuf, valueBuf, true, nullptr);        // [H,T,D] -> [T,H,D]
+
+    valueBuf.shape = rows;
+    m->inp[1].shape = rows;
+    cmdbuf_mat_mul(device, encoder, nullptr, nullptr, valueBuf, l.wo, m->inp[1], 1);             // :404
+    m->inp[6].shape = rows; m->inp[2].shape = rows; m->inp[3].shape = rows;
+    cmdbuf_addition(device, encoder, nullptr, nullptr, m->inp[1], m->inp[6], m->inp[2]);
+    thk_copy(device, m->inp[3].gpu, 0, m->inp[2].gpu, 0, bytes);
+    cmdbuf_rms_norm(device, encoder, nullptr, nullptr, m->inp[2]);
+    cmdbuf_row_element_multiply(device, encoder, nullptr, nullptr, m->inp[2], l.ffn_norm);
+
+    m->ffWorking[0].shape.r = T;
+    m->ffWorking[1].shape.r = T;
+    std::swap(l.w1.shape.r, l.w1.shape.c);                                                       // :427-428: B described as [K, N]
+    std::swap(l.w3.shape.r, l.w3.shape.c);
+    cmdbuf_mat_mul(device, encoder, nullptr, nullptr, m->inp[2], l.w1, m->ffWorking[0], 1);
+    cmdbuf_mat_mul(device, encoder, nullptr, nullptr, m->inp[2], l.w3, m->ffWorking[1], 1);
+    cmdbuf_silu(device, encoder, nullptr, nullptr, m->ffWorking[0]);
+    cmdbuf_element_mult_in_place(device, encoder, nullptr, nullptr, m->ffWorking[0], m->ffWorking[1]);
+    std::swap(l.w2.shape.r, l.w2.shape.c);                                                       // :444
+    cmdbuf_mat_mul(device, encoder, nullptr, nullptr, m->ffWorking[0], l.w2, m->inp[2], 1);
+    m->inp[0].shape = rows;
+    cmdbuf_addition(device, encoder, nullptr, nullptr, m->inp[3], m->inp[2], m->inp[0]);
+    thk_copy(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, bytes);
+    reset_layer_tensors(l);
+}
+
 // th-llama.cpp:270-452, n_tokens == 1 branch.  Buffer roles as in the reference: inp0 = x (normed in
 // place), inp6 = residual copy, inp1..3 = Q/K/V, inp4 = Q^T, inp5 = scores.
 void build_layer_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, std::shared_ptr<LlamaModel> m, LlamaLayer& l,
                         LlamaLayerComputePipeline& p, int n_tokens, int n_past) {
     reset_working_memory_tensors(*m);
     reset_layer_tensors(l);
-    if (n_tokens != 1) { fprintf(stderr, "build_layer_cmdbuf: the op graph evaluates one token at a time\n"); return; }
+    if (n_tokens != 1) { build_layer_cmdbuf_batch(device, encoder, m, l, n_tokens, n_past); return; }
 
     TensorBuffer& queryBuf = m->inp[1];
     TensorBuffer& keyBuf = m->inp[2];
@@ -212,6 +284,38 @@ static bool eval_one_opgraph(WGPUDevice device, WGPUQueue queue, std::shared_ptr
     return true;
 }
 
+// n_tokens > 1 in one pass (the reference's 8-token `pb` path, th-llama.cpp:600-608, for any size <= n_batch)
+static bool eval_batch_opgraph(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens, int T,
+                               int n_past) {
+    if (!write_uniforms(queue, m, T, n_past)) return false;
+    reset_working_memory_tensors(*m);
+    m->inp[0].shape = TensorShape{0, 0, 1, m->n_embd};
+    const int64_t stride = (int64_t)m->n_embd * (int64_t)get_TensorType_size(m->tok_embeddings.type);
+    TensorBuffer& emb = m->tok_embeddings;
+    const TensorShape keep = emb.shape;
+    emb.shape = TensorShape{0, 0, 1, m->n_embd};
+    bool ok = true;
+    for (int i = 0; i < T && ok; ++i) {             // embedding rows -> inp0 (th-llama.cpp:552-575)
+        if (tokens[i] < 0 || tokens[i] >= m->n_vocab) { ok = false; break; }
+        ok = cmdbuf_f16_f32_conversion(device, kEncoder, nullptr, nullptr, m->inp[0], emb, 4, (int)(i * m->n_embd * 4),
+                                       (int)(stride * tokens[i])).is_valid();
+    }
+    emb.shape = keep;
+    if (!ok) return false;
+    thk_copy(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, (size_t)T * m->n_embd * sizeof(float));
+    const int64_t H = m->n_head, D = m->n_embd / m->n_head;
+    for (auto& l : m->layers) {
+        build_layer_cmdbuf(device, kEncoder, m, l, m->pb, T, n_past);
+        if (thk_kv_to_hpd(device, (const float*)l.key_cache.gpu, (float*)l.key_cache_hpd.gpu, n_past, T, m->n_ctx, H, D)) return false;
+        if (thk_kv_to_hpd(device, (const float*)l.value_cache.gpu, (float*)l.value_cache_hpd.gpu, n_past, T, m->n_ctx, H, D)) return false;
+    }
+    reset_working_memory_tensors(*m);
+    LlamaFinalComputePipeline pf;                                     // uncached: shapes depend on the batch size
+    pf.p01.buildPipelineFlag = pf.p02.buildPipelineFlag = pf.p03.buildPipelineFlag = pf.p03_reduce.buildPipelineFlag = false;
+    build_final_compute_cmdbuf(device, kEncoder, m, pf, T);          // logits of the last row (aOffset)
+    return thk_gemm_check(device) == THK_OK;
+}
+
 tk_llama_token th_eval_gpu(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens,
                            int n_tokens, int n_past) {
     if (th_eval_gpu_launch(device, queue, m, tokens, n_tokens, n_past) != 0) return -1;
@@ -229,6 +333,16 @@ int th_eval_gpu_launch(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Llama
     }
     const int64_t launches0 = g_launch_count;
     int64_t fused_launches = 0;
+    if (n_tokens > 1 && m->tp_size == 1 && m->batchPrefill) {
+        // batched prompt: chunks of up to n_batch tokens through the op graph with tensor-core matmuls, then the
+        // new KV rows are handed to the fused decoder's cache layout
+        for (int t0 = 0; t0 < n_tokens; t0 += m->n_batch) {
+            const int T = std::min<int>(m->n_batch, n_tokens - t0);
+            if (!eval_batch_opgraph(device, queue, m, tokens + t0, T, n_past + t0)) { fprintf(stderr, "th_eval_gpu: batched prefill failed\n"); return -1; }
+        }
+        m->gpuLaunches = g_launch_count - launches0;
+        return 0;
+    }
     for (int i = 0; i < n_tokens; ++i) {
         const tk_llama_token tok = tokens[i];
         if (tok < 0 || tok >= m->n_vocab) { fprintf(stderr, "th_eval_gpu: token %d outside the vocabulary\n", tok); return -1; }

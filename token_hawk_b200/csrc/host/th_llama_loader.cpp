@@ -171,9 +171,9 @@ void post_load_init_model(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Ll
     m->working_key_cache = TensorBuffer(kvShape, TensorType_F32, device);   // :338-339
     m->working_val_cache = TensorBuffer(kvShape, TensorType_F32, device);
     // inp[5] holds the scores [n_head][1][n_ctx]; the reference's [8, n_embd] only covers ctx 512 (:341-344)
-    int64_t inpCols = E;
-    const int64_t need = (H * (int64_t)m->n_ctx + m->n_batch - 1) / m->n_batch;
-    if (need > inpCols) inpCols = need;
+    if (m->n_batch > m->n_ctx) m->n_batch = m->n_ctx;
+    int64_t inpCols = E;                       // per row; scores need n_head * n_batch * n_ctx floats in total
+    if (Hl * (int64_t)m->n_ctx > inpCols) inpCols = Hl * (int64_t)m->n_ctx;
     for (int i = 0; i < LlamaModel::nInpBuffers; ++i) {
         m->inp[i] = TensorBuffer(TensorShape{0, 0, m->n_batch, inpCols}, TensorType_F32, device);
         m->inp[i].shape = m->inp[i].originalShape = TensorShape{0, 0, m->n_batch, E};

@@ -430,3 +430,26 @@ extern "C" int thk_fill_kv(thk_ctx* ctx, float* dst, uint64_t seed, uint64_t tid
     THK_LAUNCH_CHECK();
     return THK_OK;
 }
+
+// -------------------------------------------------------------------------------------------
+// KV rows [pos0, pos0+npos) from the reference layout [pos][head][dim] into the fused decoder's
+// [head][n_ctx][dim] layout (after a batched prefill through the op graph; no reference analogue --
+// the reference re-transposes the whole cache every token instead, th-llama.cpp:353-354)
+// -------------------------------------------------------------------------------------------
+__global__ void kv_to_hpd_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t pos0, int64_t npos, int64_t n_ctx,
+                                 int64_t H, int64_t D) {
+    const int64_t total = npos * H * D;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = i % D, h = (i / D) % H, pz = i / (D * H);
+        dst[(h * n_ctx + pos0 + pz) * D + d] = src[((pos0 + pz) * H + h) * D + d];
+    }
+}
+extern "C" int thk_kv_to_hpd(thk_ctx* ctx, const float* src_phd, float* dst_hpd, int64_t pos0, int64_t npos, int64_t n_ctx, int64_t H,
+                             int64_t D) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx && src_phd && dst_hpd, "thk_kv_to_hpd: null argument");
+    THK_CHECK_ARG(pos0 >= 0 && npos > 0 && pos0 + npos <= n_ctx && H > 0 && D > 0, "thk_kv_to_hpd: bad range");
+    kv_to_hpd_kernel<<<ew_blocks(ctx, npos * H * D), 256, 0, ctx->stream>>>(src_phd, dst_hpd, pos0, npos, n_ctx, H, D);
+    THK_LAUNCH_CHECK();
+    return THK_OK;
+}

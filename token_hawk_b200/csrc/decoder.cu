@@ -75,6 +75,7 @@ struct DecParams {
     int att_tpos;                       // positions per attention tile
     int att_max_split;
     unsigned long long timeout_ns;
+    int l2_ahead;                       // producer prefetches ahead into L2 at phase start (THK_L2_AHEAD=0 disables)
     // tensor parallel exchange (tp_size > 1): every rank owns one region laid out as
     //   float xb[2][tp][n_embd] | float amax_val[tp] | int amax_idx[tp] | unsigned flags[tp] | unsigned flags2[tp]
     // and writes its partial vectors / argmax candidates straight into every peer's region over NVLink.
@@ -197,17 +198,31 @@ __device__ __forceinline__ int xs_index(int col) {
 // ------------------------------------------------------------------------------------------
 // this CTA's share of a phase: contiguous row-group range [g0, g1)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cta_groups(const PhaseDesc& d, int& g0, int& g1) {
-    const unsigned G = (unsigned)d.G, n = gridDim.x, b = blockIdx.x;
-    g0 = (int)((G * b) / n);
-    g1 = (int)((G * (b + 1)) / n);
-}
-__device__ __forceinline__ void locate_group(const PhaseDesc& d, int g, int& segi, int& lg) {
-    segi = 0; lg = g;
-    if (!d.paired) {
-        while (segi < 2 && lg >= d.gs[segi]) { lg -= d.gs[segi]; ++segi; }
+// Rows, not row groups, are divided between the CTAs: CTA b owns the (even-aligned) row range
+// [R*b/n, R*(b+1)/n) of the concatenated segments and walks it in groups of up to RT rows; its last
+// group may be short.  With R/n = 83 (QKV) or 27.7 (Wo, W2) rows per CTA this balances the phase to
+// ~1-4% where whole 8-row groups left up to 33% (4 groups vs 3) -- the arrival skew at the barrier.
+struct RowIt {
+    int r, r_end;              // current / end row in the concatenated row space (paired: rows of segment 0)
+    int si, row0, nrows;       // segment, first row within it, rows in this group
+    __device__ __forceinline__ void init(const PhaseDesc& d) {
+        const unsigned total = (unsigned)(d.paired ? d.rows[0] : d.rows[0] + d.rows[1] + d.rows[2]);
+        const unsigned n = gridDim.x, b = blockIdx.x;
+        r = (int)(((total * b) / n) & ~1u);
+        r_end = (b + 1 == n) ? (int)total : (int)(((total * (b + 1)) / n) & ~1u);
+        place(d);
     }
-}
+    __device__ __forceinline__ bool valid() const { return r < r_end; }
+    __device__ __forceinline__ void place(const PhaseDesc& d) {
+        if (r >= r_end) return;
+        int off = 0;
+        si = 0;
+        if (!d.paired) { while (si < 2 && r >= off + d.rows[si]) { off += d.rows[si]; ++si; } }
+        row0 = r - off;
+        nrows = min(min(d.RT, d.rows[si] - row0), r_end - r);
+    }
+    __device__ __forceinline__ void next(const PhaseDesc& d) { r += nrows; place(d); }
+};
 
 // ------------------------------------------------------------------------------------------
 // PRODUCER
@@ -228,26 +243,52 @@ struct Ring {
     __device__ __forceinline__ uint32_t empty_bar() const { return empty_base + sl * 8; }
 };
 
-__device__ __forceinline__ bool produce_mat_phase(const DecParams& p, Ring& ring, const PhaseDesc& d, const uint16_t* w0p,
+// While the consumers sit in a grid barrier + prologue (~5 us) the ring (160 KB) fills up and the
+// producer would go idle -- and with it HBM.  At the start of a phase the producer therefore also
+// asks L2 for the next kL2Ahead bytes of this CTA's rows beyond what the ring can hold; after the
+// stall those tiles stream from L2 faster than HBM could deliver them.
+constexpr uint32_t kL2Ahead = 256u * 1024u;
+__device__ __forceinline__ void l2_prefetch_block(const void* base, uint32_t bytes, uint32_t skip, uint32_t amount, int lane) {
+    if (bytes <= skip) return;
+    const uint32_t end = min(bytes, skip + amount);
+    for (uint32_t off = skip + (uint32_t)lane * 16384u; off < end; off += 32u * 16384u)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)base + off), "r"(min(16384u, end - off)) : "memory");
+}
+
+__device__ __forceinline__ bool produce_mat_phase(const DecParams& p, Ring& ring, const PhaseDesc& dref, const uint16_t* w0p,
                                                const uint16_t* w1p, const uint16_t* w2p) {
     const int lane = threadIdx.x & 31;
-    int g0, g1;
-    cta_groups(d, g0, g1);
+    const PhaseDesc d = dref;
+    const bool prof = p.prof != nullptr;
     const int C = d.C;
-    for (int g = g0; g < g1; ++g) {
-        int segi, lg;
-        locate_group(d, g, segi, lg);
+    RowIt it;
+    if (p.l2_ahead) {
+        it.init(d);
+        if (it.valid()) {
+            const uint32_t ring_bytes = kNumSlots * kSlotBytes;
+            if (d.paired) {                        // rows [row0, ..) of both matrices, consumed alternately
+                const uint32_t bytes = (uint32_t)(it.r_end - it.r) * (uint32_t)C * 2u;
+                l2_prefetch_block(w0p + (size_t)it.row0 * C, bytes, ring_bytes / 2, kL2Ahead / 2, lane);
+                l2_prefetch_block(w1p + (size_t)it.row0 * C, bytes, ring_bytes / 2, kL2Ahead / 2, lane);
+            } else {                               // the CTA's rows are one contiguous block (per segment)
+                const uint16_t* w = it.si == 0 ? w0p : it.si == 1 ? w1p : w2p;
+                const uint32_t rows_here = (uint32_t)min(it.r_end - it.r, d.rows[it.si] - it.row0);
+                l2_prefetch_block(w + (size_t)it.row0 * C, rows_here * (uint32_t)C * 2u, ring_bytes, kL2Ahead, lane);
+            }
+        }
+    }
+    for (it.init(d); it.valid(); it.next(d)) {
         const int nsub = d.paired ? 2 : 1;
         for (int sub = 0; sub < nsub; ++sub) {
-            const int si = d.paired ? sub : segi;
-            const int row0 = lg * d.RT;
-            const int nrows = min(d.RT, d.rows[si] - row0);
+            const int si = d.paired ? sub : it.si;
+            const int row0 = it.row0;
+            const int nrows = it.nrows;
             for (int kt = 0; kt < d.KT; ++kt) {
                 const int col0 = kt * d.CT;
                 const int ncols = min(d.CT, C - col0);
-                const long long t0 = p.prof ? clock64() : 0;
+                const long long t0 = prof ? clock64() : 0;
                 if (!mbar_wait(p, ring.empty_bar(), ring.empty_parity(), 1)) return false;
-                if (p.prof) ring.wait_cyc += clock64() - t0;
+                if (prof) ring.wait_cyc += clock64() - t0;
                 const uint32_t dst = ring.slot_addr(), fb = ring.full_bar();
                 if (lane == 0) mbar_expect_tx(fb, (uint32_t)nrows * ncols * 2u);
                 __syncwarp();
@@ -361,11 +402,12 @@ __device__ __forceinline__ void grid_barrier(Cons& c, int xset = -1, unsigned ep
     bar_sync(BAR_ALL, kMathThreads + 32);
     ++c.nbar;
     if (c.ct == 0) {
-        red_release_add(c.p.bar_ctr, 1u);
+        unsigned* const ctr = c.p.bar_ctr;              // read the parameter block once, not per poll
+        red_release_add(ctr, 1u);
         const unsigned target = c.nbar * gridDim.x;
         unsigned long long t0 = 0;
         unsigned it = 0;
-        while (ld_acquire_u32(c.p.bar_ctr) < target) {
+        while (ld_acquire_u32(ctr) < target) {
             if ((++it & 63u) == 0u) {
                 if (t0 == 0) t0 = gtimer();
                 if (aborted(c.p)) break;
@@ -541,32 +583,30 @@ __device__ __forceinline__ float reduce_rows(float (&v)[kRC], int lane) {
 
 // ---- math warps: stream tiles, leave per-warp partial row sums in sm->red[buf] for the epilogue warp ----
 template <int RPW, int CPW>
-__device__ __forceinline__ void math_mat_phase_t(Cons& c, const PhaseDesc& d) {
+__device__ __forceinline__ void math_mat_phase_t(Cons& c, const PhaseDesc& dref) {
     const DecParams& p = c.p;
-    int g0, g1;
-    cta_groups(d, g0, g1);
+    const PhaseDesc d = dref;                      // one read of the parameter block; the loops below use registers
+    const bool prof = p.prof != nullptr;
     const int WC = d.WC, C = d.C;
     const int wr = c.cw / WC, wc = c.cw % WC;
     constexpr int kLog = (RPW == 8) ? 3 : (RPW == 4) ? 2 : (RPW == 2) ? 1 : 0;
     unsigned gq = 0;                                            // (group, sub) pairs handed to the epilogue warp
-    for (int g = g0; g < g1; ++g) {
-        int segi, lg;
-        locate_group(d, g, segi, lg);
+    bool first = true;
+    RowIt it;
+    for (it.init(d); it.valid(); it.next(d)) {
         const int nsub = d.paired ? 2 : 1;
         for (int sub = 0; sub < nsub; ++sub) {
-            const int si = d.paired ? sub : segi;
-            const int row0 = lg * d.RT;
-            const int nrows = min(d.RT, d.rows[si] - row0);
+            const int nrows = it.nrows;
             float acc[kRC][2];
 #pragma unroll
             for (int r = 0; r < kRC; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
             for (int kt = 0; kt < d.KT; ++kt) {
                 const int col0 = kt * d.CT;
                 const int ncols = min(d.CT, C - col0);
-                const long long w0 = p.prof ? clock64() : 0;
+                const long long w0 = prof ? clock64() : 0;
                 if (c.ok) c.ok = mbar_wait(p, c.ring.full_bar(), c.ring.full_parity(), 3);
-                if (p.prof) c.ring.wait_cyc += clock64() - w0;
-                if (g == g0 && sub == 0 && kt == 0) prof_mark(c, PROF_FIRST_TILE);
+                if (prof) c.ring.wait_cyc += clock64() - w0;
+                if (first) { if (prof) prof_mark(c, PROF_FIRST_TILE); first = false; }
                 if (c.ok) tile_fma<RPW, CPW>(c.slots + (size_t)c.ring.slot() * kSlotBytes, c.xs, WC, wr, wc, c.lane, col0, nrows, ncols, acc);
                 __syncwarp();
                 if (c.lane == 0) mbar_arrive(c.ring.empty_bar());
@@ -595,23 +635,23 @@ __device__ __forceinline__ void math_mat_phase_t(Cons& c, const PhaseDesc& d) {
 enum EpiKind { EPI_QKV, EPI_WO, EPI_W13, EPI_W2, EPI_OUT };
 struct EpiState { float gate[2]; float best; int best_idx; };
 
-__device__ __forceinline__ void epi_mat_phase(Cons& c, const PhaseDesc& d, EpiKind kind, const thk_llama_layer* L, EpiState& es) {
+__device__ __forceinline__ void epi_mat_phase(Cons& c, const PhaseDesc& dref, EpiKind kind, const thk_llama_layer* L, EpiState& es) {
     const DecParams& p = c.p;
-    int g0, g1;
-    cta_groups(d, g0, g1);
-    const int WC = d.WC, D = p.head_dim;
+    const PhaseDesc d = dref;
+    const int WC = d.WC, D = p.head_dim, tp_size = p.tp_size, tp_rank = p.tp_rank, n_ctx = p.n_ctx, n_past = p.n_past, Vl = p.Vl;
+    float* const px = p.x; float* const ph1 = p.h1; float* const pq = p.q; float* const pff = p.ff; float* const plogits = p.logits;
+    float* const kcache = L ? L->key_cache : nullptr; float* const vcache = L ? L->value_cache : nullptr;
     unsigned gq = 0;
-    for (int g = g0; g < g1; ++g) {
-        int segi, lg;
-        locate_group(d, g, segi, lg);
+    RowIt it;
+    for (it.init(d); it.valid(); it.next(d)) {
         const int nsub = d.paired ? 2 : 1;
         for (int sub = 0; sub < nsub; ++sub) {
-            const int si = d.paired ? sub : segi;
-            const int row0 = lg * d.RT;
-            const int nrows = min(d.RT, d.rows[si] - row0);
+            const int si = d.paired ? sub : it.si;
+            const int row0 = it.row0;
+            const int nrows = it.nrows;
             float resid[2] = {0.f, 0.f};
-            if ((kind == EPI_WO || kind == EPI_W2) && p.tp_size == 1) {   // residual operand: load before waiting for the sums
-                const float* rs = (kind == EPI_WO) ? p.x : p.h1;
+            if ((kind == EPI_WO || kind == EPI_W2) && tp_size == 1) {   // residual operand: load before waiting for the sums
+                const float* rs = (kind == EPI_WO) ? px : ph1;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) { const int t = c.lane + 32 * k; if (t < nrows) resid[k] = __ldcg(rs + row0 + t); }
             }
@@ -627,34 +667,34 @@ __device__ __forceinline__ void epi_mat_phase(Cons& c, const PhaseDesc& d, EpiKi
                 switch (kind) {
                 case EPI_QKV:
                     if (si == 2) {                                   // V: append (th-llama.cpp:338)
-                        L->value_cache[((size_t)(r / D) * p.n_ctx + p.n_past) * D + (r % D)] = y;
+                        vcache[((size_t)(r / D) * n_ctx + n_past) * D + (r % D)] = y;
                     } else if ((t & 1) == 0) {                       // Q / K: rotate the pair (t, t+1), th.cpp:1457-1492
                         float y1 = 0.f;
                         for (int w = 0; w < WC; ++w) y1 += c.sm->red[buf][w][t + 1];
                         const float2 cs = c.sm->rope[(r % D) >> 1];
                         const float a = y * cs.x - y1 * cs.y, b = y * cs.y + y1 * cs.x;
-                        if (si == 0) { p.q[r] = a; p.q[r + 1] = b; }
+                        if (si == 0) { pq[r] = a; pq[r + 1] = b; }
                         else {
-                            float* kc = L->key_cache + ((size_t)(r / D) * p.n_ctx + p.n_past) * D + (r % D);
+                            float* kc = kcache + ((size_t)(r / D) * n_ctx + n_past) * D + (r % D);
                             kc[0] = a; kc[1] = b;                    // th-llama.cpp:337
                         }
                     }
                     break;
                 case EPI_WO:                                                           // th-llama.cpp:409
-                    if (p.tp_size == 1) p.h1[r] = resid[k] + y;
-                    else for (int dst = 0; dst < p.tp_size; ++dst) xb_ptr(p, dst, 0, p.tp_rank)[r] = y;   // partial -> every rank
+                    if (tp_size == 1) ph1[r] = resid[k] + y;
+                    else for (int dst = 0; dst < tp_size; ++dst) xb_ptr(p, dst, 0, tp_rank)[r] = y;   // partial -> every rank
                     break;
                 case EPI_W13:
                     if (sub == 0) es.gate[k] = y;
-                    else { const float gv = es.gate[k]; p.ff[r] = (gv / (1.0f + expf(-gv))) * y; }   // :436,:438
+                    else { const float gv = es.gate[k]; pff[r] = (gv / (1.0f + expf(-gv))) * y; }   // :436,:438
                     break;
                 case EPI_W2:                                                           // th-llama.cpp:447
-                    if (p.tp_size == 1) p.x[r] = resid[k] + y;
-                    else for (int dst = 0; dst < p.tp_size; ++dst) xb_ptr(p, dst, 1, p.tp_rank)[r] = y;
+                    if (tp_size == 1) px[r] = resid[k] + y;
+                    else for (int dst = 0; dst < tp_size; ++dst) xb_ptr(p, dst, 1, tp_rank)[r] = y;
                     break;
                 case EPI_OUT: {
-                    if (p.logits) p.logits[r] = y;
-                    const int gid = p.tp_rank * p.Vl + r;
+                    if (plogits) plogits[r] = y;
+                    const int gid = tp_rank * Vl + r;
                     if (es.best_idx < 0 || y > es.best) { es.best = y; es.best_idx = gid; }
                 } break;
                 }
@@ -1158,6 +1198,7 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     if (p.att_tpos > kMaxTilePos) p.att_tpos = kMaxTilePos;
     p.att_max_split = d->grid / p.Hl > 0 ? d->grid / p.Hl : 1;
     p.timeout_ns = 4000000000ull;
+    p.l2_ahead = getenv("THK_L2_AHEAD") ? atoi(getenv("THK_L2_AHEAD")) : 0;   // measured: hurts (294 vs 322 tok/s), see DESIGN.md
     const int max_vec = p.n_embd > p.Fh ? p.n_embd : p.Fh;
     d->smem = decode_smem_bytes(max_vec);
     if (d->smem > 227 * 1024) {

@@ -262,7 +262,7 @@ __device__ __forceinline__ bool produce_mat_phase(const DecParams& p, Ring& ring
     const bool prof = p.prof != nullptr;
     const int C = d.C;
     RowIt it;
-    if (p.l2_ahead) {
+    if (p.l2_ahead == 1) {
         it.init(d);
         if (it.valid()) {
             const uint32_t ring_bytes = kNumSlots * kSlotBytes;
@@ -277,8 +277,22 @@ __device__ __forceinline__ bool produce_mat_phase(const DecParams& p, Ring& ring
             }
         }
     }
+    // mode 2: whenever the producer finds the ring full (steady-state back-pressure, and above all the
+    // grid-barrier + prologue stall at a phase boundary) it asks L2 for one more tile-sized chunk of this
+    // CTA's rows beyond the ring, up to kL2Ahead ahead -- HBM keeps working while the consumers cannot.
+    const bool pf_on = p.l2_ahead == 2;
+    const uint32_t ring_bytes = kNumSlots * kSlotBytes;
+    int pf_seg = -1;
+    uint32_t pf_off = 0, blk_bytes = 0;
+    int blk_row0 = 0;
     for (it.init(d); it.valid(); it.next(d)) {
         const int nsub = d.paired ? 2 : 1;
+        if (pf_on && it.si != pf_seg) {          // (re)anchor the look-ahead on this segment's block of rows
+            pf_seg = it.si;
+            blk_row0 = it.row0;
+            blk_bytes = (uint32_t)min(it.r_end - it.r, d.rows[it.si] - it.row0) * (uint32_t)C * 2u;
+            pf_off = 0;
+        }
         for (int sub = 0; sub < nsub; ++sub) {
             const int si = d.paired ? sub : it.si;
             const int row0 = it.row0;
@@ -287,6 +301,20 @@ __device__ __forceinline__ bool produce_mat_phase(const DecParams& p, Ring& ring
                 const int col0 = kt * d.CT;
                 const int ncols = min(d.CT, C - col0);
                 const long long t0 = prof ? clock64() : 0;
+                if (pf_on && !mbar_try_wait(ring.empty_bar(), ring.empty_parity())) {
+                    const uint32_t issue_off = (uint32_t)(row0 - blk_row0) * (uint32_t)C * 2u;
+                    const uint32_t lo = issue_off + (d.paired ? ring_bytes / 2 : ring_bytes);
+                    if (pf_off < lo) pf_off = lo;
+                    if (pf_off < blk_bytes && pf_off < lo + kL2Ahead) {
+                        const uint32_t n = min(32768u, blk_bytes - pf_off);
+                        if (lane == 0) {
+                            const uint16_t* b0 = (d.paired ? w0p : (si == 0 ? w0p : si == 1 ? w1p : w2p)) + (size_t)blk_row0 * C;
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)b0 + pf_off), "r"(n) : "memory");
+                            if (d.paired) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)(w1p + (size_t)blk_row0 * C) + pf_off), "r"(n) : "memory");
+                        }
+                        pf_off += n;
+                    }
+                }
                 if (!mbar_wait(p, ring.empty_bar(), ring.empty_parity(), 1)) return false;
                 if (prof) ring.wait_cyc += clock64() - t0;
                 const uint32_t dst = ring.slot_addr(), fb = ring.full_bar();

@@ -11,9 +11,9 @@ NAMES = ["qkv", "att", "wo", "w13", "w2"]
 
 
 def summarize(marks, prod, n_layer, ctx, verbose=False):
-    # phase p (= barriers passed): 0 embed; 1+5l+k layer phases; 1+5L out; 2+5L argmax
-    start, pro, first, last, arrive, fenced, waitc = (marks[:, :, i] for i in range(7))
-    nph = 2 + 5 * n_layer
+    # phase p (= grid barriers passed): 5l+k layer phases (k: qkv, att, wo, w13, w2); 5L logits; 5L+1 = end of kernel
+    start, pro, first, last, arrive, prod_last, waitc, prod_first = (marks[:, :, i] for i in range(8))
+    nph = 1 + 5 * n_layer
     out = {}
 
     def stats(ph_list, bytes_per_phase):
@@ -24,7 +24,7 @@ def summarize(marks, prod, n_layer, ctx, verbose=False):
             dur = nxt.max() - s.min()                      # phase wall time
             skew = a.max() - a.min()                       # arrival skew at the closing barrier
             lat = nxt.min() - a.max()                      # last arrival -> first pass
-            fence = np.median(fenced[:, ph] - a)
+            fence = np.median(np.where(prod_first[:, ph] > 0, prod_first[:, ph] - s, 0))   # producer's first issue relative to phase start (negative: ahead)
             prol = np.median(np.where(pro[:, ph] > 0, pro[:, ph] - s, 0))
             ft = np.median(np.where(first[:, ph] > 0, first[:, ph] - np.maximum(pro[:, ph], s), 0))
             span = np.where(last[:, ph] > 0, last[:, ph] - first[:, ph], 0)
@@ -32,16 +32,15 @@ def summarize(marks, prod, n_layer, ctx, verbose=False):
         r = np.array(rows, dtype=np.float64)
         m = r.mean(0)
         return {"us": m[0] / 1e3, "ideal_us_at_6.57TBps": bytes_per_phase / 6.5732e12 * 1e6, "arrive_skew_us": m[1] / 1e3,
-                "barrier_latency_us": m[2] / 1e3, "fence_us": m[3] / 1e3, "prologue_us": m[4] / 1e3, "first_tile_wait_us": m[5] / 1e3,
+                "barrier_latency_us": m[2] / 1e3, "producer_lead_us": -m[3] / 1e3, "prologue_us": m[4] / 1e3, "first_tile_wait_us": m[5] / 1e3,
                 "tile_span_med_us": m[6] / 1e3, "tile_span_max_us": m[7] / 1e3, "consumer_ring_wait_kcyc": m[8] / 1e3}
 
     mb = {"qkv": 3 * E * E * 2, "att": 2 * ctx * E * 4, "wo": E * E * 2, "w13": 2 * E * F * 2, "w2": E * F * 2}
     for k, n in enumerate(NAMES):
-        out[n] = stats([1 + 5 * l + k for l in range(n_layer)], mb[n])
+        out[n] = stats([5 * l + k for l in range(n_layer)], mb[n])
         out[n]["total_us"] = out[n]["us"] * n_layer
         out[n]["GBps"] = mb[n] / (out[n]["us"] * 1e-6) / 1e9
-    out["out"] = stats([1 + 5 * n_layer], V * E * 2)
-    out["embed_us"] = float(start[:, 1].max() - start[:, 0].min()) / 1e3
+    out["out"] = stats([5 * n_layer], V * E * 2)
     out["kernel_us"] = float(start[:, nph].max() - start[:, 0].min()) / 1e3
     out["producer_wait_frac_med"] = float(np.median(prod[:, 0] / np.maximum(prod[:, 1], 1)))
     out["producer_tiles_med"] = float(np.median(prod[:, 2]))

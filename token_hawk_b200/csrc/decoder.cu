@@ -106,9 +106,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+// weights and KV are read once per token: evict-first in L2, so the stream does not push the small hot
+// data (activation vectors, gains, split results, barrier counters, code) out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     unsigned v;
@@ -146,8 +153,8 @@ __device__ __forceinline__ unsigned* xflags(const DecParams& p, int rank, int se
 
 constexpr int kProfPhases = 256;
 enum ProfSlot { PROF_START = 0, PROF_PROLOGUE = 1, PROF_FIRST_TILE = 2, PROF_LAST_TILE = 3, PROF_ARRIVE = 4, PROF_PROD_LAST = 5, PROF_WAIT_FULL = 6, PROF_PROD_FIRST = 7 };
-__device__ __forceinline__ void prof_store(const DecParams& p, unsigned phase, int slot, unsigned long long v) {
-    if (phase < (unsigned)kProfPhases) p.prof[((size_t)blockIdx.x * kProfPhases + phase) * 8 + slot] = v;
+__device__ __noinline__ void prof_mark(unsigned long long* prof, unsigned phase, int slot) {   // out of line: ~25 call sites
+    if (phase < (unsigned)kProfPhases) prof[((size_t)blockIdx.x * kProfPhases + phase) * 8 + slot] = gtimer();
 }
 
 __device__ __forceinline__ bool aborted(const DecParams& p) { return ld_volatile_u32(p.status) != 0; }
@@ -206,6 +213,12 @@ __device__ __forceinline__ Smem carve(unsigned char* base) {
     s.red_full_a = smem_u32(&s.misc->red_full[0]);
     s.red_free_a = smem_u32(&s.misc->red_free[0]);
     return s;
+}
+
+// every function that is kept out of line re-derives the carve-up from the dynamic shared memory base
+__device__ __forceinline__ Smem smem_view() {
+    extern __shared__ __align__(1024) unsigned char smem_base[];
+    return carve(smem_base);
 }
 
 // conflict-free activation layout: 256-col chunk c, lane l owns cols 8l..8l+7; its first float4 sits
@@ -287,6 +300,7 @@ struct Prod {
     bool dead;
     unsigned tiles;
     long long wait_cyc;
+    uint64_t pol;
 };
 __device__ __forceinline__ void wait_empty(const DecParams& p, const Smem& S, Prod& c, unsigned tag) {
     if (c.dead) return;
@@ -312,18 +326,18 @@ __device__ __forceinline__ void produce_mat_phase(const DecParams& p, const Smem
                 const int col0 = kt * CT;
                 const int ncols = min(CT, C - col0);
                 wait_empty(p, S, c, 1);
-                if (p.prof && first && lane == 0) { prof_store(p, phase_idx, PROF_PROD_FIRST, gtimer()); first = false; }
+                if (p.prof && first && lane == 0) { prof_mark(p.prof, phase_idx, PROF_PROD_FIRST); first = false; }
                 const uint32_t fb = S.full_a + c.ring.sl * 8, dst = S.slots_a + c.ring.sl * kSlotBytes;
                 const uint32_t row_bytes = (uint32_t)ncols * 2u;
                 if (lane == 0) mbar_expect_tx(fb, (uint32_t)it.nrows * row_bytes);
                 __syncwarp();
-                if (lane < it.nrows) bulk_g2s(dst + (uint32_t)lane * row_bytes, wrow + (size_t)lane * C + col0, row_bytes, fb);
+                if (lane < it.nrows) bulk_g2s(dst + (uint32_t)lane * row_bytes, wrow + (size_t)lane * C + col0, row_bytes, fb, c.pol);
                 c.ring.advance();
                 ++c.tiles;
             }
         }
     }
-    if (p.prof && lane == 0) prof_store(p, phase_idx, PROF_PROD_LAST, gtimer());
+    if (p.prof && lane == 0) prof_mark(p.prof, phase_idx, PROF_PROD_LAST);
 }
 
 __device__ __forceinline__ void produce_att_phase(const DecParams& p, const Smem& S, Prod& c, const thk_llama_layer& L, unsigned phase_idx) {
@@ -341,24 +355,24 @@ __device__ __forceinline__ void produce_att_phase(const DecParams& p, const Smem
             const uint32_t bytes = (uint32_t)np * D * 4u;
             for (int kv = 0; kv < 2; ++kv) {
                 wait_empty(p, S, c, 2);
-                if (p.prof && first && lane == 0) { prof_store(p, phase_idx, PROF_PROD_FIRST, gtimer()); first = false; }
+                if (p.prof && first && lane == 0) { prof_mark(p.prof, phase_idx, PROF_PROD_FIRST); first = false; }
                 const float* base = (kv == 0 ? L.key_cache : L.value_cache) + ((size_t)h * p.n_ctx + pos) * D;
                 const uint32_t fb = S.full_a + c.ring.sl * 8;
-                if (lane == 0) { mbar_expect_tx(fb, bytes); bulk_g2s(S.slots_a + c.ring.sl * kSlotBytes, base, bytes, fb); }
+                if (lane == 0) { mbar_expect_tx(fb, bytes); bulk_g2s(S.slots_a + c.ring.sl * kSlotBytes, base, bytes, fb, c.pol); }
                 __syncwarp();
                 c.ring.advance();
                 ++c.tiles;
             }
         }
     }
-    if (p.prof && lane == 0) prof_store(p, phase_idx, PROF_PROD_LAST, gtimer());
+    if (p.prof && lane == 0) prof_mark(p.prof, phase_idx, PROF_PROD_LAST);
 }
 
 __device__ __forceinline__ int phase_of(int k) { return k == K_QKV ? PH_QKV : k == K_WO ? PH_WO : k == K_W13 ? PH_W13 : k == K_W2 ? PH_W2 : PH_OUT; }
 
 __device__ void producer_main(const DecParams& p, const Smem& S) {
     const long long t0 = clock64();
-    Prod c{{0u, 0u}, false, 0u, 0};
+    Prod c{{0u, 0u}, false, 0u, 0, l2_evict_first_policy()};
     const int nsteps = 5 * p.n_layer + 1;
     int l = 0, k = K_QKV;                                 // same step order as the consumers
     for (int i = 0; i < nsteps; ++i) {
@@ -404,7 +418,9 @@ __device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S
     float* dump_lane = S.red + cw * (kRows * 32) + lane;
     bool first = p.prof != nullptr && cw == 0 && lane == 0;
     RowIt it;
-    for (it.init(d); it.valid(); it.next(d)) {
+    it.init(d);
+    if (first) prof_mark(p.prof, phase_idx, PROF_WAIT_FULL);     // schedule computed, about to wait for the first tile
+    for (; it.valid(); it.next(d)) {
         for (int sub = 0; sub < nsub; ++sub) {
             float acc[kRows][2];
 #pragma unroll
@@ -413,7 +429,7 @@ __device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S
                 const int col0 = kt * CT;
                 const int ncols = min(CT, C - col0);
                 wait_full(p, S, c, 3);
-                if (first) { prof_store(p, phase_idx, PROF_FIRST_TILE, gtimer()); first = false; }
+                if (first) { prof_mark(p.prof, phase_idx, PROF_FIRST_TILE); first = false; }
                 if (col < ncols) {
                     const float4 x0 = *(const float4*)(xlane + col0);
                     const float4 x1 = *(const float4*)(xlane + col0 + 128);
@@ -441,7 +457,7 @@ __device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S
             ++gq;
         }
     }
-    if (p.prof && cw == 0 && lane == 0) prof_store(p, phase_idx, PROF_LAST_TILE, gtimer());
+    if (p.prof && cw == 0 && lane == 0) prof_mark(p.prof, phase_idx, PROF_LAST_TILE);
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -578,12 +594,28 @@ __device__ __forceinline__ float4 load_summed(const DecParams& p, const float* s
 }
 // xs <- rmsnorm(v) * gain (cmdbuf_rms_norm + cmdbuf_row_element_multiply, th.cpp:1153-1200,1298-1315; under
 // tensor parallelism the residual adds of th-llama.cpp:409/447 move here).  When `out` is given, v is also
-// written back as the new residual stream, each float4 by exactly one CTA.  greg: this thread's first 4
-// float4s of the gain, loaded before the grid barrier.
+// written back as the new residual stream, each float4 by exactly one CTA.  The gain was L2-prefetched
+// before the grid barrier.
 __device__ __forceinline__ void prologue_norm(const DecParams& p, const Smem& S, const float* src, const uint16_t* emb_row, const float* gain,
-                                              const float4 (&greg)[4], int n, int which, float* out, int ct, int cw, int lane) {
+                                              int n, int which, float* out, int ct, int cw, int lane) {
+    // All of a thread's loads are issued before the first use: one L2 round trip (~0.5 us under the weight
+    // stream) instead of one per loop iteration.  4 float4 per thread cover n <= 4096; the tail loop is generic.
+    float4 v[4], greg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = (ct + k * kMathThreads) * 4;
+        if (i < n) { v[k] = load_summed(p, src, emb_row, which, i); greg[k] = __ldg((const float4*)(gain + i)); }
+    }
     float ss = 0.f;
-    for (int i = ct * 4; i < n; i += kMathThreads * 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = (ct + k * kMathThreads) * 4;
+        if (i < n) {
+            ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss); ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
+            if (out && (unsigned)(i >> 2) % gridDim.x == blockIdx.x) *(float4*)(out + i) = v[k];
+        }
+    }
+    for (int i = (ct + 4 * kMathThreads) * 4; i < n; i += kMathThreads * 4) {      // n > 4096: stash the raw values in xs
         const float4 t = load_summed(p, src, emb_row, which, i);
         ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
         *(float4*)(S.xs + xs_index(i)) = t;
@@ -596,11 +628,18 @@ __device__ __forceinline__ void prologue_norm(const DecParams& p, const Smem& S,
 #pragma unroll
     for (int w = 0; w < kMathWarps; ++w) tot += S.misc->norm_part[w];
     const float inv = 1.0f / sqrtf(tot / (float)n + 1e-6f);
-    int k = 0;
-    for (int i = ct * 4; i < n; i += kMathThreads * 4, ++k) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = (ct + k * kMathThreads) * 4;
+        if (i < n) {
+            float4 o;
+            o.x = (v[k].x * inv) * greg[k].x; o.y = (v[k].y * inv) * greg[k].y; o.z = (v[k].z * inv) * greg[k].z; o.w = (v[k].w * inv) * greg[k].w;
+            *(float4*)(S.xs + xs_index(i)) = o;
+        }
+    }
+    for (int i = (ct + 4 * kMathThreads) * 4; i < n; i += kMathThreads * 4) {
         float4* xp = (float4*)(S.xs + xs_index(i));
-        const float4 t = *xp;
-        const float4 g = k == 0 ? greg[0] : k == 1 ? greg[1] : k == 2 ? greg[2] : k == 3 ? greg[3] : __ldg((const float4*)(gain + i));
+        const float4 t = *xp, g = __ldg((const float4*)(gain + i));
         float4 o;
         o.x = (t.x * inv) * g.x; o.y = (t.y * inv) * g.y; o.z = (t.z * inv) * g.z; o.w = (t.w * inv) * g.w;
         *xp = o;
@@ -608,29 +647,50 @@ __device__ __forceinline__ void prologue_norm(const DecParams& p, const Smem& S,
     bar_sync(BAR_MATH, kMathThreads);
 }
 __device__ __forceinline__ void prologue_copy(const Smem& S, const float* src, int n, int ct) {
-    for (int i = ct * 4; i < n; i += kMathThreads * 4)
-        *(float4*)(S.xs + xs_index(i)) = __ldcg((const float4*)(src + i));
+    constexpr int kB = 4;                                    // loads in flight per thread
+    for (int i0 = ct * 4; i0 < n; i0 += kB * kMathThreads * 4) {
+        float4 v[kB];
+#pragma unroll
+        for (int k = 0; k < kB; ++k) { const int i = i0 + k * kMathThreads * 4; if (i < n) v[k] = __ldcg((const float4*)(src + i)); }
+#pragma unroll
+        for (int k = 0; k < kB; ++k) { const int i = i0 + k * kMathThreads * 4; if (i < n) *(float4*)(S.xs + xs_index(i)) = v[k]; }
+    }
     bar_sync(BAR_MATH, kMathThreads);
 }
 // xs <- attention output of the local heads: merge the KV splits of every head (softmax denominators included)
 __device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Smem& S, int ct) {
+    // One float4 of one head per round, the loads of <= 4 splits in flight together (an L2 round trip costs ~0.5 us under
+    // the weight stream, so 4096 floats take four of them).  Wider rounds would halve that, but their register footprint
+    // tips ptxas into a pressure-limited schedule for the WHOLE kernel that serialises the weight loads of the hot loop.
     const AttSched a = make_att(p);
     const int D = p.head_dim, ps = part_stride(p);
     for (int i = ct * 4; i < p.Eh; i += kMathThreads * 4) {
         const int h = i / D, d = i - h * D;
         const float* ph = p.part + (size_t)h * a.S * ps;
-        float ms[kMaxSplit];
-        float M = -INFINITY;
-#pragma unroll
-        for (int s = 0; s < kMaxSplit; ++s) if (s < a.S) { ms[s] = __ldcg(ph + s * ps); M = fmaxf(M, ms[s]); }
-        float lt = 0.f;
+        float M = -INFINITY, lt = 0.f;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < a.S; s0 += 4) {
+            float2 ml[4];
+            float4 v[4];
 #pragma unroll
-        for (int s = 0; s < kMaxSplit; ++s) if (s < a.S) {
-            const float e = expf(ms[s] - M);
-            lt = fmaf(__ldcg(ph + s * ps + 1), e, lt);
-            const float4 v = __ldcg((const float4*)(ph + s * ps + 4 + d));
-            o.x = fmaf(v.x, e, o.x); o.y = fmaf(v.y, e, o.y); o.z = fmaf(v.z, e, o.z); o.w = fmaf(v.w, e, o.w);
+            for (int t = 0; t < 4; ++t) if (s0 + t < a.S) {
+                const float* q = ph + (s0 + t) * ps;
+                ml[t] = __ldcg((const float2*)q);
+                v[t] = __ldcg((const float4*)(q + 4 + d));
+            }
+            float Mn = M;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (s0 + t < a.S) Mn = fmaxf(Mn, ml[t].x);
+            const float c0 = expf(M - Mn);                   // first round: exp(-inf) = 0
+            lt *= c0;
+            o.x *= c0; o.y *= c0; o.z *= c0; o.w *= c0;
+            M = Mn;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (s0 + t < a.S) {
+                const float e = expf(ml[t].x - M);
+                lt = fmaf(ml[t].y, e, lt);
+                o.x = fmaf(v[t].x, e, o.x); o.y = fmaf(v[t].y, e, o.y); o.z = fmaf(v[t].z, e, o.z); o.w = fmaf(v[t].w, e, o.w);
+            }
         }
         o.x /= lt; o.y /= lt; o.z /= lt; o.w /= lt;
         *(float4*)(S.xs + xs_index(i)) = o;
@@ -638,12 +698,9 @@ __device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Sme
     bar_sync(BAR_MATH, kMathThreads);
 }
 
-__device__ __forceinline__ void load_gain(float4 (&greg)[4], const float* gain, int n, int ct) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = (ct + k * kMathThreads) * 4;
-        if (i < n) greg[k] = __ldg((const float4*)(gain + i));
-    }
+__device__ __forceinline__ void prefetch_gain(const float* gain, int n, int ct) {
+    for (int off = ct * 32; off < n; off += kMathThreads * 32)       // one 128-byte line per thread
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(gain + off));
 }
 
 __device__ void math_main(const DecParams& p, const Smem& S) {
@@ -655,9 +712,7 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
     if (tok < 0 || tok >= p.n_vocab) { if (ct == 0) raise_abort(p, 0x300u, (unsigned)tok, 0); tok = 0; }
     const uint16_t* emb_row = p.emb + (size_t)tok * p.n_embd;
     if (blockIdx.x == 0 && ct == 0) *p.bar_next = 0u;   // arm the next launch's barrier counter
-    float4 greg[4];
-    load_gain(greg, p.layers[0].attention_norm, p.n_embd, ct);
-    if (prof) prof_store(p, 0, PROF_START, gtimer());
+    if (prof) prof_mark(p.prof, 0, PROF_START);
     const int nsteps = 5 * p.n_layer + 1;
     const bool tp = p.tp_size > 1;
     int l = 0, k = K_QKV;
@@ -672,24 +727,24 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
             const float* src = i == 0 ? nullptr : (k == K_W13) ? (tp ? p.x : p.h1) : (tp ? p.h1 : p.x);
             const int which = (i == 0 || !tp) ? -1 : (k == K_W13 ? 0 : 1);
             float* out = i == 0 ? p.x : !tp ? nullptr : (k == K_W13 ? p.h1 : p.x);
-            prologue_norm(p, S, src, emb_row, gain, greg, p.n_embd, which, out, ct, cw, lane);
+            prologue_norm(p, S, src, emb_row, gain, p.n_embd, which, out, ct, cw, lane);
         } else if (k == K_WO) {
             prologue_att_merge(p, S, ct);
         } else if (k == K_W2) {
             prologue_copy(S, p.ff, p.Fh, ct);
         }
-        if (prof) prof_store(p, (unsigned)i, PROF_PROLOGUE, gtimer());
+        if (prof) prof_mark(p.prof, (unsigned)i, PROF_PROLOGUE);
         // ---- tiles ----
         if (k == K_ATT) math_att_phase(p, S, c, *L, ct, cw, lane);
         else math_mat_phase(p, S, c, p.ph[phase_of(k)], gq, cw, lane, (unsigned)i);
         if (k == K_OUT) break;
         // ---- next phase's gain while the grid barrier forms ----
-        if (k == K_WO) load_gain(greg, L->ffn_norm, p.n_embd, ct);
-        else if (k == K_W2) load_gain(greg, l + 1 < p.n_layer ? p.layers[l + 1].attention_norm : p.norm, p.n_embd, ct);
-        if (prof) prof_store(p, (unsigned)i, PROF_ARRIVE, gtimer());
+        if (k == K_WO) prefetch_gain(L->ffn_norm, p.n_embd, ct);
+        else if (k == K_W2) prefetch_gain(l + 1 < p.n_layer ? p.layers[l + 1].attention_norm : p.norm, p.n_embd, ct);
+        if (prof) prof_mark(p.prof, (unsigned)i, PROF_ARRIVE);
         if (k == K_ATT) bar_sync(BAR_PRE, kMathThreads + 32);    // our global writes (split results) precede the epilogue warp's arrive
         bar_sync(BAR_ALL, kMathThreads + 32);                     // the epilogue warp has passed the grid barrier
-        if (prof) prof_store(p, (unsigned)i + 1, PROF_START, gtimer());
+        if (prof) prof_mark(p.prof, (unsigned)i + 1, PROF_START);
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
     }
 }
@@ -888,12 +943,11 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
             if (p.next_logit) *p.next_logit = gv;
         }
     }
-    if (p.prof && lane == 0) prof_store(p, 5u * (unsigned)p.n_layer + 1u, PROF_START, gtimer());
+    if (p.prof && lane == 0) prof_mark(p.prof, 5u * (unsigned)p.n_layer + 1u, PROF_START);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_constant__ DecParams p) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const Smem S = carve(smem);
+    const Smem S = smem_view();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNumSlots; ++i) {
             mbar_init(S.full_a + i * 8, 1);
@@ -971,7 +1025,7 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     THK_CHECK_ARG(tp <= 8 && dims->tp_rank >= 0 && dims->tp_rank < tp, "thk_decoder_create: tp_size %d / tp_rank %d unsupported (1..8)", tp, dims->tp_rank);
     THK_CHECK_ARG(dims->n_embd > 0 && dims->n_head > 0 && dims->n_embd % dims->n_head == 0, "bad n_embd/n_head");
     const int D = dims->n_embd / dims->n_head;
-    THK_CHECK_ARG(D % 4 == 0 && D <= kMaxHeadDim && D % 2 == 0, "head_dim %d unsupported (need multiple of 4, <= %d)", D, kMaxHeadDim);
+    THK_CHECK_ARG(D % 16 == 0 && D <= kMaxHeadDim, "head_dim %d unsupported (need a multiple of 16, <= %d)", D, kMaxHeadDim);
     THK_CHECK_ARG(dims->n_embd % 8 == 0 && dims->n_ff % 8 == 0, "n_embd and n_ff must be multiples of 8 (16-byte f16 rows)");
     THK_CHECK_ARG(dims->n_head % tp == 0 && dims->n_ff % tp == 0 && dims->n_vocab % tp == 0, "tp_size must divide n_head, n_ff, n_vocab");
     THK_CHECK_ARG(dims->n_ctx > 0 && dims->n_layer > 0 && dims->n_vocab > 0, "bad dims");

@@ -185,6 +185,11 @@ int thk_decoder_check(thk_decoder* dec);
  * enabled, CTA 0 stores %globaltimer (ns) at kernel start [0] and after grid barrier k [k]; host_out
  * (may be NULL) receives the first n entries of the last launch. */
 int thk_decoder_profile(thk_decoder* dec, int enable, unsigned long long* host_out, int n);
+/* tuning knobs of the persistent kernel (no reference analogue; scripts/tune.py sweeps them on the GPU):
+ *   "l2_ahead_kb"  KB of a CTA's upcoming rows the producer warp asks L2 for at a phase boundary (0 = off)
+ *   "prof_phase"   phase index whose per-tile issue / retire times thk_decoder_profile records
+ * Takes effect at the next step.  Unknown key -> THK_E_INVALID. */
+int thk_decoder_tune(thk_decoder* dec, const char* key, int value);
 /* tensor-parallel wiring: peer pointers obtained by the host via CUDA IPC (or same-process P2P).
  * peer_bufs[r] / peer_flags[r] are device-visible addresses of rank r's exchange buffer / flag
  * array as returned by thk_decoder_exchange_info on that rank. */

@@ -149,6 +149,7 @@ def host() -> C.CDLL:
         H.capi_stream.argtypes = [vp]
         H.capi_fill_kv.argtypes = [vp, u64, C.c_int]
         H.capi_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.c_int]
+        H.capi_tune.argtypes = [vp, C.c_char_p, C.c_int]
         H.capi_hidden.argtypes = [vp, f32p]
         H.capi_tensor_info.restype = i64
         H.capi_tensor_info.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
@@ -361,13 +362,22 @@ class LlamaModel:
         when fetch is set; slots: 0 phase start, 1 prologue end, 2 first tile ready, 3 last tile done,
         4 barrier arrive, 5 after fence, 6 consumer ring-wait cycles."""
         grid = self.dev.sm_count
-        n = grid * 256 * 8 + grid * 4 if fetch else 0
+        n0, n1, nt = grid * 256 * 8, grid * 4, grid * 64
+        n = n0 + n1 + 2 * nt if fetch else 0
         buf = np.zeros(max(n, 1), dtype=np.uint64)
         if host().capi_profile(self.h, int(enable), buf.ctypes.data_as(C.POINTER(C.c_uint64)) if fetch else None, n):
             raise ThkError(-1, host().capi_last_error().decode())
         if not fetch:
             return None
-        return buf[:grid * 256 * 8].reshape(grid, 256, 8).astype(np.int64), buf[grid * 256 * 8:].reshape(grid, 4).astype(np.int64)
+        # per-tile times of the phase selected with tune("prof_phase", k): [cta][64] retired, [cta][64] issued
+        self.last_tile_times = (buf[n0 + n1:n0 + n1 + nt].reshape(grid, 64).astype(np.int64),
+                                buf[n0 + n1 + nt:].reshape(grid, 64).astype(np.int64))
+        return buf[:n0].reshape(grid, 256, 8).astype(np.int64), buf[n0:n0 + n1].reshape(grid, 4).astype(np.int64)
+
+    def tune(self, key: str, value: int):
+        """Persistent-kernel tuning knob (thk_decoder_tune): 'l2_ahead_kb', 'poll_depth'."""
+        if host().capi_tune(self.h, key.encode(), int(value)):
+            raise ThkError(-1, host().capi_last_error().decode())
 
     # enqueue-only calls for stream timing
     def set_token(self, tok: int):

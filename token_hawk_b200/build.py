@@ -13,15 +13,16 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-# THK_MATH_WARPS=8|16 selects the decode kernel's math-warp count; non-default variants build into lib<N>/
-_MW = os.environ.get("THK_MATH_WARPS", "")
-LIB = os.path.join(PKG, "lib" + _MW)
+# A/B variants: THK_VARIANT=<name> builds into lib_<name>/ with the extra nvcc flags in THK_DEFINES ("-DX -DY=2");
+# load one with THK_LIBDIR=lib_<name> (token_hawk_b200/__init__.py)
+_VAR = os.environ.get("THK_VARIANT", "")
+LIB = os.path.join(PKG, "lib" + ("_" + _VAR if _VAR else ""))
 INC = os.path.join(ROOT, "include")
 
 CU_SOURCES = ["context.cu", "ops.cu", "decoder.cu", "gemm_tc.cu"]
 HOST_SOURCES = ["host/th.cpp", "host/th_llama.cpp", "host/th_llama_loader.cpp", "host/capi.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-I" + INC, "-I" + CSRC] + (["-DTHK_MATH_WARPS=" + _MW] if _MW else [])
+              "-Xcompiler", "-fPIC", "-I" + INC, "-I" + CSRC] + os.environ.get("THK_DEFINES", "").split()
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra", "-I" + INC]
 

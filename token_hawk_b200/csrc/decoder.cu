@@ -21,14 +21,17 @@
 //
 // Arithmetic follows oracle/th_oracle.c (the restatement of the WGSL); only summation order
 // differs.  No tensor cores: at M=1 the work is 1 FLOP/byte and HBM-bound.
+#include <stddef.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
 namespace {
 
 constexpr int kSlotBytes = 32 * 1024;
-constexpr int kNumSlots = 5;
+constexpr int kNumSlots = 4;                          // measured on B200: 3 -> 2.83, 4 -> 2.72, 5 -> 2.75 ms/token (deeper rings queue more
+                                                      // traffic ahead of the latency-critical barrier / prologue loads)
 constexpr int kMathWarps = 8;
 constexpr int kMathThreads = kMathWarps * 32;
 constexpr int kMathBase = 32;                         // warp 0 = producer, warps 1..8 = math, warp 9 = epilogue
@@ -37,6 +40,7 @@ constexpr int kRows = 8;                              // rows per row group (= p
 constexpr int kMaxTilePos = 128;                      // attention: positions per tile cap
 constexpr int kMaxHeadDim = 128;
 constexpr int kMaxSplit = 8;                          // attention: KV splits per head cap
+constexpr int kDumpBufs = 8;                          // row-group hand-off ring between the math warps and the epilogue warp
 enum NamedBarrier { BAR_ALL = 1, BAR_MATH = 2, BAR_PRE = 3 };
 
 // Host-computed tile schedule of one matvec phase
@@ -76,6 +80,8 @@ struct DecParams {
     // and writes its partial vectors / argmax candidates straight into every peer's region over NVLink.
     unsigned char* xchg[8];             // region base per rank (peer-mapped pointers; [tp_rank] is local)
     unsigned epoch_base;                // flags are monotonic: exchange k of this launch uses epoch_base + k + 1
+    unsigned l2_ahead;                  // bytes of this CTA's rows the producer asks L2 for when a phase boundary stalls the ring (0: off)
+    int prof_phase;                     // timeline: phase whose per-tile consume / issue times are recorded (kProfTiles each)
     unsigned long long* prof;           // optional timeline: [cta][phase<256][8] u64 (see ProfSlot), then [cta][4] producer stats
 };
 
@@ -130,6 +136,23 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// shared-memory access by 32-bit shared-window address (no generic-pointer conversion on the hot path)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void st_release_sys(unsigned* ptr, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
@@ -152,9 +175,20 @@ __device__ __forceinline__ unsigned* xflags(const DecParams& p, int rank, int se
 }
 
 constexpr int kProfPhases = 256;
+constexpr int kProfTiles = 64;   // after the producer stats: [cta][kProfTiles] tile-retired times, then [cta][kProfTiles] tile-issued times
 enum ProfSlot { PROF_START = 0, PROF_PROLOGUE = 1, PROF_FIRST_TILE = 2, PROF_LAST_TILE = 3, PROF_ARRIVE = 4, PROF_PROD_LAST = 5, PROF_WAIT_FULL = 6, PROF_PROD_FIRST = 7 };
+__device__ __noinline__ void prof_tile(unsigned long long* prof, int which, int tile) {        // which: 0 retired, 1 issued
+    prof[(size_t)gridDim.x * (kProfPhases * 8 + 4 + which * kProfTiles) + (size_t)blockIdx.x * kProfTiles + tile] = gtimer();
+}
 __device__ __noinline__ void prof_mark(unsigned long long* prof, unsigned phase, int slot) {   // out of line: ~25 call sites
     if (phase < (unsigned)kProfPhases) prof[((size_t)blockIdx.x * kProfPhases + phase) * 8 + slot] = gtimer();
+}
+
+// math warps: `pm` is non-null only in the one thread that records.  The store goes through the out-of-line prof_mark:
+// an inlined %globaltimer read is hoisted by ptxas above barriers and waits (measured: phase starts recorded ~3 us
+// early), a call is a scheduling fence.
+__device__ __forceinline__ void mark(unsigned long long* pm, const DecParams& p, unsigned phase, int slot) {
+    if (pm != nullptr) prof_mark(p.prof, phase, slot);
 }
 
 __device__ __forceinline__ bool aborted(const DecParams& p) { return ld_volatile_u32(p.status) != 0; }
@@ -183,23 +217,26 @@ __device__ __noinline__ bool mbar_wait_slow(const DecParams& p, uint32_t bar, ui
 struct SmemMisc {
     unsigned long long full[kNumSlots];
     unsigned long long empty[kNumSlots];
-    unsigned long long red_full[2];     // partial-sum dump `buf` written by all math warps
-    unsigned long long red_free[2];     // ... and consumed by the epilogue warp
+    unsigned long long red_full[kDumpBufs];   // row-group sums `buf` written by all math warps
+    unsigned long long red_free[kDumpBufs];   // ... and consumed by the epilogue warp
     float norm_part[kMathWarps];
     float2 rope[kMaxHeadDim / 2];       // (cos, sin) of n_past * theta_i for this token
+    int range[5][2];                    // this CTA's row range [r, r_end) of every matvec phase (computed once per launch)
 };
 constexpr int kMiscBytes = 1024;
 static_assert(sizeof(SmemMisc) <= kMiscBytes, "SmemMisc too large");
-constexpr int kRedFloats = kMathWarps * kRows * 32;            // one dump: [warp][row][lane]
-constexpr int kRedBytes = 2 * kRedFloats * 4;                  // double buffered (16 KB)
+constexpr int kRedFloats = kMathWarps * kRows;                 // one row-group hand-off: [warp][row] warp-level sums
+constexpr int kAttScratchOff = kDumpBufs * kRedFloats;         // attention scratch (floats) behind the hand-off ring
+constexpr int kRedBytes = 8 * 1024;                            // ring (2 KB) + attention scratch (<= 6 KB)
+static_assert(kAttScratchOff * 4 + (kMathWarps * kMaxHeadDim + 2 * kMathWarps + 2 * kMaxHeadDim) * 4 <= kRedBytes, "attention scratch does not fit");
 constexpr int kXsOffset = kNumSlots * kSlotBytes + kMiscBytes + kRedBytes;
 
 struct Smem {
     unsigned char* slots;
     SmemMisc* misc;
-    float* red;       // [2][kMathWarps][kRows][32]; attention reuses it as scratch
+    float* red;       // [kDumpBufs][kMathWarps][kRows] hand-off ring, then the attention scratch
     float* xs;
-    uint32_t slots_a, full_a, empty_a, red_full_a, red_free_a;   // shared-window addresses
+    uint32_t slots_a, full_a, empty_a, red_full_a, red_free_a, red_a, xs_a;   // shared-window addresses
 };
 __device__ __forceinline__ Smem carve(unsigned char* base) {
     Smem s;
@@ -207,11 +244,17 @@ __device__ __forceinline__ Smem carve(unsigned char* base) {
     s.misc = (SmemMisc*)(base + kNumSlots * kSlotBytes);
     s.red = (float*)(base + kNumSlots * kSlotBytes + kMiscBytes);
     s.xs = (float*)(base + kXsOffset);
-    s.slots_a = smem_u32(base);
-    s.full_a = smem_u32(&s.misc->full[0]);
-    s.empty_a = smem_u32(&s.misc->empty[0]);
-    s.red_full_a = smem_u32(&s.misc->red_full[0]);
-    s.red_free_a = smem_u32(&s.misc->red_free[0]);
+    // The shared-window address of the base is read ONCE and made opaque: otherwise every use re-derives it from the
+    // generic pointer (S2UR SR_CgaCtaId + ULEA, ~35 cycles of latency each -- three times per tile in the hot loop).
+    uint32_t a = smem_u32(base);
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    s.slots_a = a;
+    s.full_a = a + kNumSlots * kSlotBytes + (uint32_t)offsetof(SmemMisc, full);
+    s.empty_a = a + kNumSlots * kSlotBytes + (uint32_t)offsetof(SmemMisc, empty);
+    s.red_full_a = a + kNumSlots * kSlotBytes + (uint32_t)offsetof(SmemMisc, red_full);
+    s.red_free_a = a + kNumSlots * kSlotBytes + (uint32_t)offsetof(SmemMisc, red_free);
+    s.red_a = a + kNumSlots * kSlotBytes + kMiscBytes;
+    s.xs_a = a + kXsOffset;
     return s;
 }
 
@@ -221,12 +264,8 @@ __device__ __forceinline__ Smem smem_view() {
     return carve(smem_base);
 }
 
-// conflict-free activation layout: 256-col chunk c, lane l owns cols 8l..8l+7; its first float4 sits
-// at (c*64 + l)*16 B and its second at (c*64 + 32 + l)*16 B.
-__device__ __forceinline__ int xs_index(int col) {
-    const int within = col & 255;
-    return (col & ~255) + ((within & 4) << 5) + ((within >> 3) << 2) + (within & 3);
-}
+// activation layout in xs: 256-col chunk c, lane l owns cols 8l..8l+7; its first float4 (cols 8l..8l+3) sits at
+// (c*64 + l)*16 B and its second at (c*64 + 32 + l)*16 B -- consecutive lanes hit consecutive banks (conflict free).
 
 // ring position shared by producer and consumers (kept incrementally: no modulo per tile)
 struct Ring {
@@ -257,23 +296,33 @@ __device__ __forceinline__ void release_slot(const Smem& S, Cons& c, int lane) {
 struct RowIt {
     int r, r_end;              // current / end row in the concatenated row space (paired: rows of segment 0)
     int si, row0, nrows;       // segment, first row within it, rows in this group
-    __device__ __forceinline__ void init(const PhaseDesc& d) {
+    int e0, e1;                // end of segment 0 / segment 1 in the concatenated row space (registers: an indexed
+                               // constant-bank read per segment test costs ~60 cycles of latency at every row-group end)
+    // even-aligned contiguous share of the phase's rows; the two divisions cost ~0.3 us of dependent latency, so the
+    // kernel evaluates this once per launch and phase kind (SmemMisc::range) instead of at every phase start
+    static __device__ __forceinline__ void share(const PhaseDesc& d, int& r0, int& r1) {
         const unsigned total = (unsigned)(d.paired ? d.rows[0] : d.rows[0] + d.rows[1] + d.rows[2]);
         const unsigned n = gridDim.x, b = blockIdx.x;
-        r = (int)(((total * b) / n) & ~1u);
-        r_end = (b + 1 == n) ? (int)total : (int)(((total * (b + 1)) / n) & ~1u);
-        place(d);
+        r0 = (int)(((total * b) / n) & ~1u);
+        r1 = (b + 1 == n) ? (int)total : (int)(((total * (b + 1)) / n) & ~1u);
+    }
+    __device__ __forceinline__ void init(const SmemMisc* misc, int ph, const PhaseDesc& d) {
+        r = misc->range[ph][0];
+        r_end = misc->range[ph][1];
+        e0 = d.paired ? 0x7fffffff : d.rows[0];
+        e1 = d.paired ? 0x7fffffff : d.rows[0] + d.rows[1];
+        place();
     }
     __device__ __forceinline__ bool valid() const { return r < r_end; }
-    __device__ __forceinline__ void place(const PhaseDesc& d) {
-        if (r >= r_end) return;
-        int off = 0;
-        si = 0;
-        if (!d.paired) { while (si < 2 && r >= off + d.rows[si]) { off += d.rows[si]; ++si; } }
-        row0 = r - off;
-        nrows = min(min(kRows, d.rows[si] - row0), r_end - r);
+    __device__ __forceinline__ void place() {
+        // a group never crosses a segment or the end of this CTA's share
+        si = r < e0 ? 0 : (r < e1 ? 1 : 2);
+        const int seg_begin = r < e0 ? 0 : (r < e1 ? e0 : e1);
+        const int seg_end = r < e0 ? e0 : (r < e1 ? e1 : 0x7fffffff);
+        row0 = r - seg_begin;
+        nrows = min(min(kRows, seg_end - r), r_end - r);
     }
-    __device__ __forceinline__ void next(const PhaseDesc& d) { r += nrows; place(d); }
+    __device__ __forceinline__ void next() { r += nrows; place(); }
 };
 
 // attention work split (shared by producer and consumers)
@@ -312,19 +361,44 @@ __device__ __forceinline__ void wait_empty(const DecParams& p, const Smem& S, Pr
     }
 }
 
-__device__ __forceinline__ void produce_mat_phase(const DecParams& p, const Smem& S, Prod& c, const PhaseDesc& d, const uint16_t* w0p,
+// bulk L2 prefetch of [base, base + bytes) spread over the lanes (SASS UBLKPF); bytes % 16 == 0
+__device__ __forceinline__ void l2_prefetch_span(const unsigned char* base, uint32_t bytes, int lane) {
+    constexpr uint32_t kPiece = 8192u;
+#pragma unroll 1
+    for (uint32_t off = (uint32_t)lane * kPiece; off < bytes; off += 32u * kPiece)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(min(kPiece, bytes - off)) : "memory");
+}
+
+__device__ __forceinline__ void produce_mat_phase(const DecParams& p, const Smem& S, Prod& c, int ph, const uint16_t* w0p,
                                                const uint16_t* w1p, const uint16_t* w2p, unsigned phase_idx) {
+    const PhaseDesc& d = p.ph[ph];
     const int lane = threadIdx.x & 31;
     const int C = d.C, KT = d.KT, CT = d.CT, nsub = d.paired ? 2 : 1;
     bool first = true;
+    int j = 0;                                  // tiles of this phase issued so far
     RowIt it;
-    for (it.init(d); it.valid(); it.next(d)) {
+    for (it.init(S.misc, ph, d); it.valid(); it.next()) {
         for (int sub = 0; sub < nsub; ++sub) {
             const int si = d.paired ? sub : it.si;
             const uint16_t* wrow = (si == 0 ? w0p : si == 1 ? w1p : w2p) + (size_t)it.row0 * C;
-            for (int kt = 0; kt < KT; ++kt) {
+            for (int kt = 0; kt < KT; ++kt, ++j) {
                 const int col0 = kt * CT;
                 const int ncols = min(CT, C - col0);
+                if (j == kNumSlots && p.l2_ahead != 0u && !c.dead && !mbar_try_wait(S.empty_a + c.ring.sl * 8, c.ring.par ^ 1u)) {
+                    // The ring now holds nothing but tiles of this phase and its first tile has not been consumed: the
+                    // consumers are still in the previous phase's tail / the grid barrier / the prologue, and the ring
+                    // (160 KB, ~3.5 us of this SM's HBM share) cannot cover that stall.  Ask L2 for this CTA's next rows
+                    // so HBM keeps streaming; after the stall the ring refills from L2 faster than HBM could feed it.
+                    const uint32_t row_bytes_full = (uint32_t)C * 2u;
+                    if (d.paired) {
+                        const uint32_t bytes = min((uint32_t)(it.r_end - it.r) * row_bytes_full, p.l2_ahead >> 1);
+                        l2_prefetch_span((const unsigned char*)(w0p + (size_t)it.row0 * C), bytes, lane);
+                        l2_prefetch_span((const unsigned char*)(w1p + (size_t)it.row0 * C), bytes, lane);
+                    } else {
+                        const uint32_t rows_left = (uint32_t)min(d.rows[si] - it.row0, it.r_end - it.r);
+                        l2_prefetch_span((const unsigned char*)wrow, min(rows_left * row_bytes_full, p.l2_ahead), lane);
+                    }
+                }
                 wait_empty(p, S, c, 1);
                 if (p.prof && first && lane == 0) { prof_mark(p.prof, phase_idx, PROF_PROD_FIRST); first = false; }
                 const uint32_t fb = S.full_a + c.ring.sl * 8, dst = S.slots_a + c.ring.sl * kSlotBytes;
@@ -332,6 +406,7 @@ __device__ __forceinline__ void produce_mat_phase(const DecParams& p, const Smem
                 if (lane == 0) mbar_expect_tx(fb, (uint32_t)it.nrows * row_bytes);
                 __syncwarp();
                 if (lane < it.nrows) bulk_g2s(dst + (uint32_t)lane * row_bytes, wrow + (size_t)lane * C + col0, row_bytes, fb, c.pol);
+                if (p.prof && (int)phase_idx == p.prof_phase && j < kProfTiles && lane == 0) prof_tile(p.prof, 1, j);
                 c.ring.advance();
                 ++c.tiles;
             }
@@ -383,7 +458,7 @@ __device__ void producer_main(const DecParams& p, const Smem& S) {
             const uint16_t* w0 = k == K_QKV ? L->wq : k == K_WO ? L->wo : k == K_W13 ? L->w1 : k == K_W2 ? L->w2 : p.out_w;
             const uint16_t* w1 = k == K_QKV ? L->wk : k == K_W13 ? L->w3 : nullptr;
             const uint16_t* w2 = k == K_QKV ? L->wv : nullptr;
-            produce_mat_phase(p, S, c, p.ph[phase_of(k)], w0, w1, w2, (unsigned)i);
+            produce_mat_phase(p, S, c, phase_of(k), w0, w1, w2, (unsigned)i);
         }
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
     }
@@ -398,66 +473,116 @@ __device__ void producer_main(const DecParams& p, const Smem& S) {
 // ------------------------------------------------------------------------------------------
 // MATH WARPS
 // ------------------------------------------------------------------------------------------
-// 8 weights (one uint4 of f16) times 8 activations into two independent accumulators
-__device__ __forceinline__ void fma8(const uint4& w, const float4& x0, const float4& x1, float& a0, float& a1) {
-    float2 f;
-    f = h2_to_f2(w.x); a0 = fmaf(x0.x, f.x, a0); a1 = fmaf(x0.y, f.y, a1);
-    f = h2_to_f2(w.y); a0 = fmaf(x0.z, f.x, a0); a1 = fmaf(x0.w, f.y, a1);
-    f = h2_to_f2(w.z); a0 = fmaf(x1.x, f.x, a0); a1 = fmaf(x1.y, f.y, a1);
-    f = h2_to_f2(w.w); a0 = fmaf(x1.z, f.x, a0); a1 = fmaf(x1.w, f.y, a1);
+// 8 weights (one uint4 of f16) times 8 activations into an accumulator PAIR, with the packed f32x2 FMA of sm_100
+// (FFMA2: two independent round-to-nearest FMAs per instruction -- bit-identical to two fmaf, half the issue slots).
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ unsigned long long cvt2(uint32_t h2) {     // exact f16x2 -> f32x2 (== th.cpp:312-333)
+    const float2 f = h2_to_f2(h2);
+    return pack2(f.x, f.y);
+}
+__device__ __forceinline__ void fma8(const uint4& w, const unsigned long long (&x)[4], unsigned long long& acc) {
+    acc = ffma2(x[0], cvt2(w.x), acc);
+    acc = ffma2(x[1], cvt2(w.y), acc);
+    acc = ffma2(x[2], cvt2(w.z), acc);
+    acc = ffma2(x[3], cvt2(w.w), acc);
+}
+
 
 // Stream this CTA's tiles of one matvec phase.  Per tile a warp owns one 256-column chunk of all 8 rows
 // (rows past a short group's end hold stale bytes; their sums are never read).  `gq` counts the row
 // groups handed to the epilogue warp since kernel start (dump buffer = gq & 1, use = gq >> 1).
-__device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S, Cons& c, const PhaseDesc& d, unsigned& gq,
-                                               int cw, int lane, unsigned phase_idx) {
+//
+// The per-tile body is the consumer's critical path: when a phase starts the ring is full and HBM idles until slots
+// come back, so the faster a tile is retired the shorter every phase boundary.  Hence: all ten 128-bit loads of a
+// tile are issued up front by shared-window address, the body is branch free (lanes past a short tile's last column
+// read column 0 against a zero activation), the math is packed FFMA2, and nothing but the ring bookkeeping remains.
+__device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S, Cons& c, int ph, unsigned& gq,
+                                               int cw, int lane, unsigned phase_idx, unsigned long long* pm) {
+    const PhaseDesc& d = p.ph[ph];
     const int C = d.C, KT = d.KT, CT = d.CT, nsub = d.paired ? 2 : 1;
-    const int col = (cw << 8) + (lane << 3);                  // this lane's first column inside a tile
-    const float* xlane = S.xs + (cw << 8) + (lane << 2);      // + col0: first float4; second at +128 floats
-    float* dump_lane = S.red + cw * (kRows * 32) + lane;
-    bool first = p.prof != nullptr && cw == 0 && lane == 0;
+    const int col = (cw << 8) + (lane << 3);                                  // this lane's first column inside a tile
+    const uint32_t xlane_a = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);   // + col0 * 4: first float4; second 512 B on
+    const uint32_t dump_a = S.red_a + (uint32_t)(cw * kRows * 4);                 // this warp's [row] record inside a hand-off buffer
+    bool first = pm != nullptr;
+    int ntile = 0;
     RowIt it;
-    it.init(d);
-    if (first) prof_mark(p.prof, phase_idx, PROF_WAIT_FULL);     // schedule computed, about to wait for the first tile
-    for (; it.valid(); it.next(d)) {
+    it.init(S.misc, ph, d);
+    mark(pm, p, phase_idx, PROF_WAIT_FULL);     // schedule computed, about to wait for the first tile
+    for (; it.valid(); it.next()) {
         for (int sub = 0; sub < nsub; ++sub) {
-            float acc[kRows][2];
+            unsigned long long acc[kRows];                    // (even-column sum, odd-column sum) per row
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
-            for (int kt = 0; kt < KT; ++kt) {
-                const int col0 = kt * CT;
+            for (int r = 0; r < kRows; ++r) acc[r] = 0ull;
+            int col0 = 0;
+            for (int kt = 0; kt < KT; ++kt, col0 += CT) {
                 const int ncols = min(CT, C - col0);
+                const bool ok = col < ncols;
+                const uint32_t stride = (uint32_t)ncols * 2u;
+                const uint32_t xa = ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4);
                 wait_full(p, S, c, 3);
-                if (first) { prof_mark(p.prof, phase_idx, PROF_FIRST_TILE); first = false; }
-                if (col < ncols) {
-                    const float4 x0 = *(const float4*)(xlane + col0);
-                    const float4 x1 = *(const float4*)(xlane + col0 + 128);
-                    const unsigned char* wp = S.slots + c.ring.sl * kSlotBytes + col * 2;
-                    const int stride = ncols * 2;
-                    uint4 w[kRows];
+                if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
+                const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (ok ? (uint32_t)col << 1 : 0u);
+                float4 x0 = lds128f(xa), x1 = lds128f(xa + 512u);
+                uint4 w[kRows];
 #pragma unroll
-                    for (int r = 0; r < kRows; ++r) w[r] = *(const uint4*)(wp + r * stride);
+                for (int r = 0; r < kRows; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
+                if (!ok) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
+                const unsigned long long xp[4] = {pack2(x0.x, x0.y), pack2(x0.z, x0.w), pack2(x1.x, x1.y), pack2(x1.z, x1.w)};
 #pragma unroll
-                    for (int r = 0; r < kRows; ++r) fma8(w[r], x0, x1, acc[r][0], acc[r][1]);
-                }
+                for (int r = 0; r < kRows; ++r) fma8(w[r], xp, acc[r]);
                 release_slot(S, c, lane);
+                if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(p.prof, 0, ntile++);
             }
-            // hand the partial sums to the epilogue warp: dump [warp][row][lane], signal, move on
-            const unsigned buf = gq & 1u, use = gq >> 1;
+            // Hand the row sums to the epilogue warp.  A transposing shuffle reduction (4 + 2 + 1 exchanges halve the rows
+            // a lane holds while doubling the lanes summed, then 2 plain steps) leaves the warp total of row (lane >> 2) & 7
+            // in every lane; 8 floats per warp go into a ring of kDumpBufs hand-off records, so the math warps can run
+            // kDumpBufs row groups ahead of the epilogue warp (whose per-group latency would otherwise pace the ring drain
+            // at a phase start).  Fixed order of additions: deterministic.
+            float v[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                float lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[r]));
+                v[r] = lo + hi;
+            }
+            {
+                const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, u4 ? v[r] : v[r + 4], 16);
+                    v[r] = (u4 ? v[r + 4] : v[r]) + recv;
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float recv = __shfl_xor_sync(0xffffffffu, u3 ? v[r] : v[r + 2], 8);
+                    v[r] = (u3 ? v[r + 2] : v[r]) + recv;
+                }
+                const float recv = __shfl_xor_sync(0xffffffffu, u2 ? v[0] : v[1], 4);
+                v[0] = (u2 ? v[1] : v[0]) + recv;
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            }
+            const unsigned buf = gq & (kDumpBufs - 1), use = gq / kDumpBufs;
             if (use > 0 && !c.dead) {
                 const uint32_t fb = S.red_free_a + buf * 8;
                 if (!mbar_try_wait(fb, (use - 1) & 1u)) c.dead = !mbar_wait_slow(p, fb, (use - 1) & 1u, 6);
             }
-            float* dst = dump_lane + buf * kRedFloats;
-#pragma unroll
-            for (int r = 0; r < kRows; ++r) dst[r * 32] = acc[r][0] + acc[r][1];
+            if ((lane & 3) == 0) sts32f(dump_a + (buf * kRedFloats + (unsigned)((lane >> 2) & 7)) * 4u, v[0]);
             __syncwarp();
             if (lane == 0) mbar_arrive(S.red_full_a + buf * 8);
             ++gq;
         }
     }
-    if (p.prof && cw == 0 && lane == 0) prof_mark(p.prof, phase_idx, PROF_LAST_TILE);
+    mark(pm, p, phase_idx, PROF_LAST_TILE);
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -476,9 +601,11 @@ __device__ __forceinline__ void math_att_phase(const DecParams& p, const Smem& S
     const int D = p.head_dim;
     const float scale = 1.0f / sqrtf((float)D);
     const bool act = lane < (D >> 2);
-    float* sc_o = S.red;                              // [8][128]
-    float* sc_m = S.red + kMathWarps * kMaxHeadDim;   // [8]
+    float* sc_o = S.red + kAttScratchOff;             // [8][128]
+    float* sc_m = sc_o + kMathWarps * kMaxHeadDim;    // [8]
     float* sc_l = sc_m + kMathWarps;                  // [8]
+    float* sc_kn = sc_l + kMathWarps;                 // [128] the new position's K row (warp 0 only)
+    float* sc_vn = sc_kn + kMaxHeadDim;               // [128] ... and V row
     for (int u = blockIdx.x; u < p.Hl * a.S; u += gridDim.x) {
         const int h = u / a.S, sp = u % a.S;
         const int pa = (int)(((long long)a.N * sp) / a.S);
@@ -486,7 +613,16 @@ __device__ __forceinline__ void math_att_phase(const DecParams& p, const Smem& S
         const int pb = min(pb_full, p.n_past);
         const bool has_new = (pb_full == a.N);
         float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act) q4 = __ldcg((const float4*)(p.q + h * D) + lane);
+        if (act) {
+            q4 = __ldcg((const float4*)(p.q + h * D) + lane);
+            if (has_new && cw == 0) {   // the token's own K/V row (QKV epilogue of this launch): same L2 round trip as q,
+                const size_t off = ((size_t)h * p.n_ctx + p.n_past) * D;     // parked in shared memory until the tiles are done
+                const float4 kn4 = __ldcg((const float4*)(L.key_cache + off) + lane);
+                const float4 vn4 = __ldcg((const float4*)(L.value_cache + off) + lane);
+                *(float4*)(sc_kn + (lane << 2)) = kn4;
+                *(float4*)(sc_vn + (lane << 2)) = vn4;
+            }
+        }
         float m = -INFINITY, lsum = 0.f;
         float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int pos = pa; pos < pb; pos += p.att_tpos) {
@@ -535,13 +671,12 @@ __device__ __forceinline__ void math_att_phase(const DecParams& p, const Smem& S
             release_slot(S, c, lane);
             release_slot(S, c, lane);
         }
-        if (has_new && cw == 0) {   // the token's own K/V row, written by the QKV epilogue of this launch
-            const size_t off = ((size_t)h * p.n_ctx + p.n_past) * D;
-            float sdot = 0.f;
+        if (has_new && cw == 0) {   // the token's own position
             float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float sdot = 0.f;
             if (act) {
-                sdot = dot4(q4, __ldcg((const float4*)(L.key_cache + off) + lane));
-                v4 = __ldcg((const float4*)(L.value_cache + off) + lane);
+                sdot = dot4(q4, *(const float4*)(sc_kn + (lane << 2)));
+                v4 = *(const float4*)(sc_vn + (lane << 2));
             }
             sdot = warp_sum(sdot) * scale;
             const float m_new = fmaxf(m, sdot);
@@ -592,80 +727,96 @@ __device__ __forceinline__ float4 load_summed(const DecParams& p, const float* s
     }
     return v;
 }
-// xs <- rmsnorm(v) * gain (cmdbuf_rms_norm + cmdbuf_row_element_multiply, th.cpp:1153-1200,1298-1315; under
-// tensor parallelism the residual adds of th-llama.cpp:409/447 move here).  When `out` is given, v is also
-// written back as the new residual stream, each float4 by exactly one CTA.  The gain was L2-prefetched
-// before the grid barrier.
-__device__ __forceinline__ void prologue_norm(const DecParams& p, const Smem& S, const float* src, const uint16_t* emb_row, const float* gain,
-                                              int n, int which, float* out, int ct, int cw, int lane) {
-    // All of a thread's loads are issued before the first use: one L2 round trip (~0.5 us under the weight
-    // stream) instead of one per loop iteration.  4 float4 per thread cover n <= 4096; the tail loop is generic.
-    float4 v[4], greg[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = (ct + k * kMathThreads) * 4;
-        if (i < n) { v[k] = load_summed(p, src, emb_row, which, i); greg[k] = __ldg((const float4*)(gain + i)); }
-    }
+// ---- prologues ----
+// A math warp only ever multiplies against ITS columns of the activation vector: chunk kt * CT/256 + cw of every K tile,
+// and within a chunk a lane only its own 8 columns.  So the staged vector xs is lane-private storage: every lane loads,
+// transforms and stores exactly the values it will read back in the tile loop -- no CTA barrier, no cross-warp traffic,
+// and a warp starts on its first tile as soon as its own loads have landed.
+__device__ __forceinline__ void sts128f(uint32_t a, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// xs <- v * gain, v = the residual stream (cmdbuf_rms_norm + cmdbuf_row_element_multiply, th.cpp:1153-1200,1298-1315; under
+// tensor parallelism the residual adds of th-llama.cpp:409/447 move here).  The RMS scale 1/sqrt(mean(v^2) + 1e-6) is a
+// scalar, so it is applied to the finished row sums by the epilogue warp instead: here every warp only leaves its share
+// of sum(v^2) in norm_part[cw].  When `out` is given, v is also written back as the new residual stream, each float4 by
+// exactly one CTA.  The gain was L2-prefetched before the grid barrier.
+__device__ __forceinline__ void prologue_norm(const DecParams& p, const Smem& S, const PhaseDesc& d, const float* src, const uint16_t* emb_row,
+                                              const float* gain, int which, float* out, int cw, int lane) {
+    const int n = d.C;
+    const int lcol = (cw << 8) + (lane << 3);                 // this lane's first column inside a K tile
+    const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
     float ss = 0.f;
+    for (int kt0 = 0; kt0 < d.KT; kt0 += 2) {                 // two K tiles (4 + 4 float4 loads) per L2 round trip
+        float4 v[4], g[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = (ct + k * kMathThreads) * 4;
-        if (i < n) {
-            ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss); ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
-            if (out && (unsigned)(i >> 2) % gridDim.x == blockIdx.x) *(float4*)(out + i) = v[k];
+        for (int u = 0; u < 2; ++u) {
+            const int c = (kt0 + u) * d.CT + lcol;
+            if (kt0 + u < d.KT && lcol < d.CT && c < n) {
+                v[2 * u] = load_summed(p, src, emb_row, which, c);
+                v[2 * u + 1] = load_summed(p, src, emb_row, which, c + 4);
+                g[2 * u] = __ldg((const float4*)(gain + c));
+                g[2 * u + 1] = __ldg((const float4*)(gain + c + 4));
+            }
         }
-    }
-    for (int i = (ct + 4 * kMathThreads) * 4; i < n; i += kMathThreads * 4) {      // n > 4096: stash the raw values in xs
-        const float4 t = load_summed(p, src, emb_row, which, i);
-        ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
-        *(float4*)(S.xs + xs_index(i)) = t;
-        if (out && (unsigned)(i >> 2) % gridDim.x == blockIdx.x) *(float4*)(out + i) = t;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = (kt0 + u) * d.CT + lcol;
+            if (kt0 + u < d.KT && lcol < d.CT && c < n) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const float4 t = v[2 * u + hh], gg = g[2 * u + hh];
+                    ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
+                    const int i = c + 4 * hh;
+                    if (out && (unsigned)(i >> 2) % gridDim.x == blockIdx.x) *(float4*)(out + i) = t;
+                    sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2) + 512u * hh, make_float4(t.x * gg.x, t.y * gg.y, t.z * gg.z, t.w * gg.w));
+                }
+            }
+        }
     }
     ss = warp_sum(ss);
     if (lane == 0) S.misc->norm_part[cw] = ss;
-    bar_sync(BAR_MATH, kMathThreads);
-    float tot = 0.f;
+}
+// xs <- src (the FFN hidden vector for W2)
+__device__ __forceinline__ void prologue_copy(const Smem& S, const PhaseDesc& d, const float* src, int cw, int lane) {
+    const int n = d.C;
+    const int lcol = (cw << 8) + (lane << 3);
+    const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
+    for (int kt0 = 0; kt0 < d.KT; kt0 += 3) {                 // three K tiles (6 float4 loads) per L2 round trip
+        float4 v[6];
 #pragma unroll
-    for (int w = 0; w < kMathWarps; ++w) tot += S.misc->norm_part[w];
-    const float inv = 1.0f / sqrtf(tot / (float)n + 1e-6f);
+        for (int u = 0; u < 3; ++u) {
+            const int c = (kt0 + u) * d.CT + lcol;
+            if (kt0 + u < d.KT && lcol < d.CT && c < n) {
+                v[2 * u] = __ldcg((const float4*)(src + c));
+                v[2 * u + 1] = __ldcg((const float4*)(src + c + 4));
+            }
+        }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = (ct + k * kMathThreads) * 4;
-        if (i < n) {
-            float4 o;
-            o.x = (v[k].x * inv) * greg[k].x; o.y = (v[k].y * inv) * greg[k].y; o.z = (v[k].z * inv) * greg[k].z; o.w = (v[k].w * inv) * greg[k].w;
-            *(float4*)(S.xs + xs_index(i)) = o;
+        for (int u = 0; u < 3; ++u) {
+            const int c = (kt0 + u) * d.CT + lcol;
+            if (kt0 + u < d.KT && lcol < d.CT && c < n) {
+                sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2), v[2 * u]);
+                sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2) + 512u, v[2 * u + 1]);
+            }
         }
     }
-    for (int i = (ct + 4 * kMathThreads) * 4; i < n; i += kMathThreads * 4) {
-        float4* xp = (float4*)(S.xs + xs_index(i));
-        const float4 t = *xp, g = __ldg((const float4*)(gain + i));
-        float4 o;
-        o.x = (t.x * inv) * g.x; o.y = (t.y * inv) * g.y; o.z = (t.z * inv) * g.z; o.w = (t.w * inv) * g.w;
-        *xp = o;
-    }
-    bar_sync(BAR_MATH, kMathThreads);
 }
-__device__ __forceinline__ void prologue_copy(const Smem& S, const float* src, int n, int ct) {
-    constexpr int kB = 4;                                    // loads in flight per thread
-    for (int i0 = ct * 4; i0 < n; i0 += kB * kMathThreads * 4) {
-        float4 v[kB];
-#pragma unroll
-        for (int k = 0; k < kB; ++k) { const int i = i0 + k * kMathThreads * 4; if (i < n) v[k] = __ldcg((const float4*)(src + i)); }
-#pragma unroll
-        for (int k = 0; k < kB; ++k) { const int i = i0 + k * kMathThreads * 4; if (i < n) *(float4*)(S.xs + xs_index(i)) = v[k]; }
-    }
-    bar_sync(BAR_MATH, kMathThreads);
-}
-// xs <- attention output of the local heads: merge the KV splits of every head (softmax denominators included)
-__device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Smem& S, int ct) {
-    // One float4 of one head per round, the loads of <= 4 splits in flight together (an L2 round trip costs ~0.5 us under
-    // the weight stream, so 4096 floats take four of them).  Wider rounds would halve that, but their register footprint
-    // tips ptxas into a pressure-limited schedule for the WHOLE kernel that serialises the weight loads of the hot loop.
+// xs <- attention output of the local heads: merge the KV splits of every head (softmax denominators included).  One
+// float4 x <= 4 splits per round (loads in flight together; ~0.6 us per L2 round trip under the weight stream): the
+// kernel sits at the 168-register ceiling of a 10-warp CTA (three warps share one SM sub-partition) and wider rounds
+// measurably slow the whole kernel down (spilled phase-loop state; measured 2.83 -> 2.92 ms/token).
+__device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Smem& S, const PhaseDesc& d, int cw, int lane) {
     const AttSched a = make_att(p);
     const int D = p.head_dim, ps = part_stride(p);
-    for (int i = ct * 4; i < p.Eh; i += kMathThreads * 4) {
-        const int h = i / D, d = i - h * D;
+    const int lcol = (cw << 8) + (lane << 3);
+    const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
+    for (int q = 0; q < 2 * d.KT; ++q) {                      // (K tile, half) -> one float4 of this lane's columns
+        const int kt = q >> 1, hh = q & 1;
+        const int c = kt * d.CT + lcol;
+        if (lcol >= d.CT || c >= d.C) continue;
+        const int i = c + 4 * hh;
+        const int h = i / D, dd = i - h * D;
         const float* ph = p.part + (size_t)h * a.S * ps;
         float M = -INFINITY, lt = 0.f;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -674,9 +825,9 @@ __device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Sme
             float4 v[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) if (s0 + t < a.S) {
-                const float* q = ph + (s0 + t) * ps;
-                ml[t] = __ldcg((const float2*)q);
-                v[t] = __ldcg((const float4*)(q + 4 + d));
+                const float* r = ph + (s0 + t) * ps;
+                ml[t] = __ldcg((const float2*)r);
+                v[t] = __ldcg((const float4*)(r + 4 + dd));
             }
             float Mn = M;
 #pragma unroll
@@ -693,9 +844,8 @@ __device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Sme
             }
         }
         o.x /= lt; o.y /= lt; o.z /= lt; o.w /= lt;
-        *(float4*)(S.xs + xs_index(i)) = o;
+        sts128f(xa + (uint32_t)((kt * d.CT) << 2) + 512u * hh, o);
     }
-    bar_sync(BAR_MATH, kMathThreads);
 }
 
 __device__ __forceinline__ void prefetch_gain(const float* gain, int n, int ct) {
@@ -705,14 +855,14 @@ __device__ __forceinline__ void prefetch_gain(const float* gain, int n, int ct) 
 
 __device__ void math_main(const DecParams& p, const Smem& S) {
     const int ct = (int)threadIdx.x - kMathBase, cw = ct >> 5, lane = ct & 31;
-    const bool prof = p.prof != nullptr && ct == 0;
+    unsigned long long* const pm = (p.prof != nullptr && ct == 0) ? p.prof + (size_t)blockIdx.x * kProfPhases * 8 : nullptr;
     Cons c{{0u, 0u}, false};
     unsigned gq = 0;
     int tok = *p.token;
     if (tok < 0 || tok >= p.n_vocab) { if (ct == 0) raise_abort(p, 0x300u, (unsigned)tok, 0); tok = 0; }
     const uint16_t* emb_row = p.emb + (size_t)tok * p.n_embd;
     if (blockIdx.x == 0 && ct == 0) *p.bar_next = 0u;   // arm the next launch's barrier counter
-    if (prof) prof_mark(p.prof, 0, PROF_START);
+    mark(pm, p, 0, PROF_START);
     const int nsteps = 5 * p.n_layer + 1;
     const bool tp = p.tp_size > 1;
     int l = 0, k = K_QKV;
@@ -727,24 +877,24 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
             const float* src = i == 0 ? nullptr : (k == K_W13) ? (tp ? p.x : p.h1) : (tp ? p.h1 : p.x);
             const int which = (i == 0 || !tp) ? -1 : (k == K_W13 ? 0 : 1);
             float* out = i == 0 ? p.x : !tp ? nullptr : (k == K_W13 ? p.h1 : p.x);
-            prologue_norm(p, S, src, emb_row, gain, p.n_embd, which, out, ct, cw, lane);
+            prologue_norm(p, S, p.ph[phase_of(k)], src, emb_row, gain, which, out, cw, lane);
         } else if (k == K_WO) {
-            prologue_att_merge(p, S, ct);
+            prologue_att_merge(p, S, p.ph[PH_WO], cw, lane);
         } else if (k == K_W2) {
-            prologue_copy(S, p.ff, p.Fh, ct);
+            prologue_copy(S, p.ph[PH_W2], p.ff, cw, lane);
         }
-        if (prof) prof_mark(p.prof, (unsigned)i, PROF_PROLOGUE);
+        mark(pm, p, (unsigned)i, PROF_PROLOGUE);
         // ---- tiles ----
         if (k == K_ATT) math_att_phase(p, S, c, *L, ct, cw, lane);
-        else math_mat_phase(p, S, c, p.ph[phase_of(k)], gq, cw, lane, (unsigned)i);
+        else math_mat_phase(p, S, c, phase_of(k), gq, cw, lane, (unsigned)i, pm);
         if (k == K_OUT) break;
         // ---- next phase's gain while the grid barrier forms ----
         if (k == K_WO) prefetch_gain(L->ffn_norm, p.n_embd, ct);
         else if (k == K_W2) prefetch_gain(l + 1 < p.n_layer ? p.layers[l + 1].attention_norm : p.norm, p.n_embd, ct);
-        if (prof) prof_mark(p.prof, (unsigned)i, PROF_ARRIVE);
+        mark(pm, p, (unsigned)i, PROF_ARRIVE);
         if (k == K_ATT) bar_sync(BAR_PRE, kMathThreads + 32);    // our global writes (split results) precede the epilogue warp's arrive
         bar_sync(BAR_ALL, kMathThreads + 32);                     // the epilogue warp has passed the grid barrier
-        if (prof) prof_mark(p.prof, (unsigned)i + 1, PROF_START);
+        mark(pm, p, (unsigned)i + 1, PROF_START);
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
     }
 }
@@ -765,7 +915,7 @@ __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, 
         const unsigned target = nbar * gridDim.x;
         unsigned long long t0 = 0;
         unsigned it = 0;
-        while (ld_relaxed_u32(ctr) < target) {
+        while (ld_relaxed_u32(ctr) < target) {    // (pipelined polling, 4 loads in flight, was measured slower: 2.80 -> 2.87 ms/token)
             if ((++it & 63u) == 0u) {
                 if (t0 == 0) t0 = gtimer();
                 if (aborted(p)) { dead = true; break; }
@@ -799,38 +949,55 @@ __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, 
 enum EpiKind { EPI_QKV, EPI_WO, EPI_W13, EPI_W2, EPI_OUT };
 struct EpiState { float gate; float best; int best_idx; };
 
-__device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S, const PhaseDesc& d, int kind, const thk_llama_layer* L,
+__device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S, int ph, int kind, const thk_llama_layer* L,
                                               EpiState& es, unsigned& gq, bool& dead, int lane) {
+    const PhaseDesc& d = p.ph[ph];
     const int D = p.head_dim, tp_size = p.tp_size, tp_rank = p.tp_rank, n_ctx = p.n_ctx, n_past = p.n_past;
     const int nsub = d.paired ? 2 : 1;
-    const int rr = lane & 7, qq = lane >> 3;          // this lane sums row rr over the dump lanes [8 qq, 8 qq + 8)
-    const float* my = S.red + rr * 32 + qq * 8;
+    const int rr = lane & 7, qq = lane >> 3;          // this lane adds row rr of math warps 2 qq and 2 qq + 1
+    const uint32_t my_a = S.red_a + (uint32_t)((2 * qq * kRows + rr) * 4);
+    const bool has_resid = (kind == EPI_WO || kind == EPI_W2) && tp_size == 1;
+    const bool need_scale = (kind == EPI_QKV || kind == EPI_W13 || kind == EPI_OUT);
+    bool have_scale = false;
+    float scale = 1.0f;
+    const float* resid_src = (kind == EPI_WO) ? p.x : p.h1;
     RowIt it;
-    for (it.init(d); it.valid(); it.next(d)) {
+    it.init(S.misc, ph, d);
+    // the residual operand of a row group is requested one group ahead: its L2 round trip (~0.6 us under the weight
+    // stream) would otherwise sit on this warp's serial per-group path
+    float resid_next = 0.f;
+    if (has_resid && it.valid() && lane < it.nrows) resid_next = __ldcg(resid_src + it.row0 + lane);
+    while (it.valid()) {
+        const int row0 = it.row0, nrows = it.nrows, si_cur = it.si;
+        it.next();                                   // `it` now describes the NEXT group
         for (int sub = 0; sub < nsub; ++sub) {
-            const int si = d.paired ? sub : it.si;
-            const int row0 = it.row0, nrows = it.nrows;
-            float resid = 0.f;
-            if ((kind == EPI_WO || kind == EPI_W2) && tp_size == 1 && lane < nrows)    // residual operand: load before waiting for the sums
-                resid = __ldcg(((kind == EPI_WO) ? p.x : p.h1) + row0 + lane);
-            const unsigned buf = gq & 1u, use = gq >> 1;
+            const int si = d.paired ? sub : si_cur;
+            const float resid = resid_next;
+            if (has_resid && it.valid() && lane < it.nrows) resid_next = __ldcg(resid_src + it.row0 + lane);
+            const unsigned buf = gq & (kDumpBufs - 1), use = gq / kDumpBufs;
             if (!dead) {
                 const uint32_t fb = S.red_full_a + buf * 8;
                 if (!mbar_try_wait(fb, use & 1u)) dead = !mbar_wait_slow(p, fb, use & 1u, 7);
             }
-            const float* src = my + buf * kRedFloats;
-            float y = 0.f;
-#pragma unroll
-            for (int w = 0; w < kMathWarps; ++w) {
-                const float4 a = *(const float4*)(src + w * (kRows * 32));
-                const float4 b = *(const float4*)(src + w * (kRows * 32) + 4);
-                y += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
-            }
+            const uint32_t src = my_a + buf * (uint32_t)(kRedFloats * 4);
+            float y = lds32f(src) + lds32f(src + kRows * 4);
             y += __shfl_xor_sync(0xffffffffu, y, 8);
             y += __shfl_xor_sync(0xffffffffu, y, 16);      // every lane: total of row (lane & 7)
             __syncwarp();
             if (lane == 0) mbar_arrive(S.red_free_a + buf * 8);
             ++gq;
+            if (need_scale) {
+                // RMSNorm scale of this phase's input (th.cpp:1153-1200): every math warp left its share of sum(v^2) before its
+                // first hand-off, so the eight parts are complete once any row group is.  Fixed order: deterministic.
+                if (!have_scale) {
+                    float tot = 0.f;
+#pragma unroll
+                    for (int w = 0; w < kMathWarps; ++w) tot += S.misc->norm_part[w];
+                    scale = 1.0f / sqrtf(tot / (float)d.C + 1e-6f);
+                    have_scale = true;
+                }
+                y *= scale;
+            }
             const float y1 = __shfl_down_sync(0xffffffffu, y, 1);     // the pair partner for RoPE
             if (lane < nrows) {
                 const int r = row0 + lane;
@@ -886,7 +1053,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
     for (int i = 0; i < nsteps; ++i) {
         if (k != K_ATT) {
             const int kind = k == K_QKV ? EPI_QKV : k == K_WO ? EPI_WO : k == K_W13 ? EPI_W13 : k == K_W2 ? EPI_W2 : EPI_OUT;
-            epi_mat_phase(p, S, p.ph[phase_of(k)], kind, k == K_OUT ? nullptr : p.layers + l, es, gq, dead, lane);
+            epi_mat_phase(p, S, phase_of(k), kind, k == K_OUT ? nullptr : p.layers + l, es, gq, dead, lane);
         } else {
             bar_sync(BAR_PRE, kMathThreads + 32);
         }
@@ -909,38 +1076,53 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
         if (lane == 0) { p.amax_val[blockIdx.x] = bv; p.amax_idx[blockIdx.x] = bi; }
         ++nbar;
         grid_barrier(p, nbar, lane, dead);
-        if (blockIdx.x == 0 && lane == 0) {
+        if (blockIdx.x == 0) {
+            // every lane takes CTAs lane, lane+32, ... (loads in flight together), then the warp reduces
             float gv = 0.f; int gi = -1;
-            for (unsigned b = 0; b < gridDim.x; ++b) {
-                const int idx = __ldcg(p.amax_idx + b);
-                if (idx < 0) continue;
-                const float v = __ldcg(p.amax_val + b);
-                if (gi < 0 || v > gv || (v == gv && idx < gi)) { gv = v; gi = idx; }
-            }
-            if (p.tp_size > 1) {
-                // cross-rank argmax: push this rank's candidate to every rank, wait for all, lowest id wins ties
-                const unsigned epoch = p.epoch_base + 2u * (unsigned)p.n_layer + 1u;
-                for (int d = 0; d < p.tp_size; ++d) { xamax_val(p, d)[p.tp_rank] = gv; xamax_idx(p, d)[p.tp_rank] = gi; }
-                __threadfence_system();
-                for (int d = 0; d < p.tp_size; ++d) st_release_sys(xflags(p, d, 1) + p.tp_rank, epoch);
-                unsigned long long t0 = 0; unsigned it = 0;
-                gv = 0.f; gi = -1;
-                for (int src = 0; src < p.tp_size; ++src) {
-                    const unsigned* f = xflags(p, p.tp_rank, 1) + src;
-                    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
-                        if ((++it & 63u) == 0u) {
-                            if (t0 == 0) t0 = gtimer();
-                            if (aborted(p)) break;
-                            if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x401u, (unsigned)src, epoch); break; }
-                        }
-                    }
-                    const int idx = __ldcv(xamax_idx(p, p.tp_rank) + src);
-                    const float v = __ldcv(xamax_val(p, p.tp_rank) + src);
-                    if (idx >= 0 && (gi < 0 || v > gv || (v == gv && idx < gi))) { gv = v; gi = idx; }
+            for (unsigned b0 = 0; b0 < gridDim.x; b0 += 128) {
+                int idx[4]; float v[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const unsigned b = b0 + (unsigned)(t * 32 + lane);
+                    idx[t] = b < gridDim.x ? __ldcg(p.amax_idx + b) : -1;
+                    v[t] = b < gridDim.x ? __ldcg(p.amax_val + b) : 0.f;
                 }
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (idx[t] >= 0 && (gi < 0 || v[t] > gv || (v[t] == gv && idx[t] < gi))) { gv = v[t]; gi = idx[t]; }
             }
-            if (p.next_token) *p.next_token = gi < 0 ? 0 : gi;
-            if (p.next_logit) *p.next_logit = gv;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, gv, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, gi, off);
+                if (oi >= 0 && (gi < 0 || ov > gv || (ov == gv && oi < gi))) { gv = ov; gi = oi; }
+            }
+            if (lane == 0) {
+                if (p.tp_size > 1) {
+                    // cross-rank argmax: push this rank's candidate to every rank, wait for all, lowest id wins ties
+                    const unsigned epoch = p.epoch_base + 2u * (unsigned)p.n_layer + 1u;
+                    for (int d = 0; d < p.tp_size; ++d) { xamax_val(p, d)[p.tp_rank] = gv; xamax_idx(p, d)[p.tp_rank] = gi; }
+                    __threadfence_system();
+                    for (int d = 0; d < p.tp_size; ++d) st_release_sys(xflags(p, d, 1) + p.tp_rank, epoch);
+                    unsigned long long t0 = 0; unsigned it = 0;
+                    gv = 0.f; gi = -1;
+                    for (int src = 0; src < p.tp_size; ++src) {
+                        const unsigned* f = xflags(p, p.tp_rank, 1) + src;
+                        while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+                            if ((++it & 63u) == 0u) {
+                                if (t0 == 0) t0 = gtimer();
+                                if (aborted(p)) break;
+                                if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x401u, (unsigned)src, epoch); break; }
+                            }
+                        }
+                        const int idx = __ldcv(xamax_idx(p, p.tp_rank) + src);
+                        const float v = __ldcv(xamax_val(p, p.tp_rank) + src);
+                        if (idx >= 0 && (gi < 0 || v > gv || (v == gv && idx < gi))) { gv = v; gi = idx; }
+                    }
+                }
+                if (p.next_token) *p.next_token = gi < 0 ? 0 : gi;
+                if (p.next_logit) *p.next_logit = gv;
+            }
         }
     }
     if (p.prof && lane == 0) prof_mark(p.prof, 5u * (unsigned)p.n_layer + 1u, PROF_START);
@@ -953,11 +1135,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
             mbar_init(S.full_a + i * 8, 1);
             mbar_init(S.empty_a + i * 8, kMathWarps);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kDumpBufs; ++i) {
             mbar_init(S.red_full_a + i * 8, kMathWarps);
             mbar_init(S.red_free_a + i * 8, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 69) {
+        const int ph = (int)threadIdx.x - 64;
+        RowIt::share(p.ph[ph], S.misc->range[ph][0], S.misc->range[ph][1]);
     }
     __syncthreads();
     if (threadIdx.x < 32) producer_main(p, S);
@@ -1054,6 +1240,9 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     p.att_max_split = d->grid / p.Hl > 0 ? d->grid / p.Hl : 1;
     if (p.att_max_split > kMaxSplit) p.att_max_split = kMaxSplit;
     p.timeout_ns = 4000000000ull;
+    p.prof_phase = -1;
+    // tuning knobs (defaults = the measured best)
+    p.l2_ahead = (unsigned)(getenv("THK_L2_AHEAD_KB") ? atoi(getenv("THK_L2_AHEAD_KB")) : 64) * 1024u;   // 0 / 64 / 128 / 192 KB: 2.765 / 2.720 / 2.744 / 2.767 ms
     const int max_vec = p.n_embd > p.Fh ? p.n_embd : p.Fh;
     d->smem = decode_smem_bytes(max_vec);
     if (d->smem > 227 * 1024) {
@@ -1152,16 +1341,24 @@ extern "C" int thk_decoder_profile(thk_decoder* d, int enable, unsigned long lon
     THK_CHECK_ARG(d, "thk_decoder_profile: null argument");
     THK_ENTER(d->ctx);
     if (enable && !d->d_prof) {
-        const size_t nprof = (size_t)d->grid * kProfPhases * 8 + (size_t)d->grid * 4;
+        const size_t nprof = (size_t)d->grid * (kProfPhases * 8 + 4 + 2 * kProfTiles);
         THK_CUDA(cudaMalloc(&d->d_prof, nprof * sizeof(unsigned long long)));
         THK_CUDA(cudaMemset(d->d_prof, 0, nprof * sizeof(unsigned long long)));
     }
     d->p.prof = enable ? d->d_prof : nullptr;
     if (host_out && n > 0 && d->d_prof) {
         THK_CUDA(cudaStreamSynchronize(d->ctx->stream));
-        const size_t nprof = (size_t)d->grid * kProfPhases * 8 + (size_t)d->grid * 4;
+        const size_t nprof = (size_t)d->grid * (kProfPhases * 8 + 4 + 2 * kProfTiles);
         THK_CUDA(cudaMemcpy(host_out, d->d_prof, sizeof(unsigned long long) * ((size_t)n > nprof ? nprof : (size_t)n), cudaMemcpyDeviceToHost));
     }
+    return THK_OK;
+}
+
+extern "C" int thk_decoder_tune(thk_decoder* d, const char* key, int value) {
+    THK_CHECK_ARG(d && key, "thk_decoder_tune: null argument");
+    if (!strcmp(key, "l2_ahead_kb")) { THK_CHECK_ARG(value >= 0 && value <= 1024, "l2_ahead_kb out of range"); d->p.l2_ahead = (unsigned)value * 1024u; }
+    else if (!strcmp(key, "prof_phase")) d->p.prof_phase = value;
+    else { thk_set_error("thk_decoder_tune: unknown key %s", key); return THK_E_INVALID; }
     return THK_OK;
 }
 

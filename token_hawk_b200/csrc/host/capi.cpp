@@ -153,6 +153,10 @@ int capi_profile(void* h, int enable, unsigned long long* out, int n) {
     auto& m = ((CapiModel*)h)->m;
     return m->decoder ? thk_decoder_profile(m->decoder, enable, out, n) : -1;
 }
+int capi_tune(void* h, const char* key, int value) {
+    auto& m = ((CapiModel*)h)->m;
+    return m->decoder ? thk_decoder_tune(m->decoder, key, value) : -1;
+}
 int capi_fill_kv(void* h, uint64_t seed, int n_positions) { return fill_kv_synthetic(((CapiModel*)h)->m, seed, n_positions) ? 0 : -1; }
 
 // residual stream after the last evaluated token's layers (fused path: decoder scratch; op graph: inp[6])

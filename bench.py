@@ -230,7 +230,7 @@ def main():
         e2e = {"value": 1e3 / ms_e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": V * 4 + (4 * world if world > 1 else 0),
                "ms_per_step": ms_e2e, "steps": ke, "api": "th_eval_gpu (capi_eval): host token id -> logits in pinned host memory -> host greedy"}
 
-    if args.phase_profile:
+    if args.phase_profile:      # needs the profiling build of the kernel library: THK_LIBDIR=lib_prof (see token_hawk_b200/build.py)
         model.profile(True)
         model.step_async(n_past)
         marks, prod = model.profile(True, fetch=True)

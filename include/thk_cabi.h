@@ -188,6 +188,8 @@ int thk_decoder_profile(thk_decoder* dec, int enable, unsigned long long* host_o
 /* tuning knobs of the persistent kernel (no reference analogue; scripts/tune.py sweeps them on the GPU):
  *   "l2_ahead_kb"  KB of a CTA's upcoming rows the producer warp asks L2 for at a phase boundary (0 = off)
  *   "prof_phase"   phase index whose per-tile issue / retire times thk_decoder_profile records
+ *   "dataflow"     1: Wo -> W13 -> W2 -> next QKV synchronise through epoch-stamped vectors instead of grid barriers (tp 1)
+ *   "poll_single"  1: a stale read of such a vector spins on the one stale element before re-reading everything
  * Takes effect at the next step.  Unknown key -> THK_E_INVALID. */
 int thk_decoder_tune(thk_decoder* dec, const char* key, int value);
 /* tensor-parallel wiring: peer pointers obtained by the host via CUDA IPC (or same-process P2P).

@@ -1,15 +1,16 @@
 #!/bin/bash
-# One gpurun call: bench line, phase profile, ctx=2048, launch list and one ncu --set full capture.
+# One gpurun call: bench line, ctx=2048, reference arm, ncu launch list and one ncu --set full capture.
+# (The in-kernel timeline needs the profiling build: THK_LIBDIR=lib_prof python scripts/tune.py --profile)
 # Usage (from the repo root on the GPU box): bash scripts/gpu_bench_profile.sh <tag>
 TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
 echo "== bench ctx=512 =="
-python bench.py --steps 200 --warmup 10 --phase-profile > $OUT/bench_${TAG}.json 2> $OUT/bench_${TAG}.err
-tail -c 3000 $OUT/bench_${TAG}.json; grep PHASES $OUT/bench_${TAG}.err
+python bench.py --steps 200 --warmup 10 > $OUT/bench_${TAG}.json 2> $OUT/bench_${TAG}.err
+tail -c 3000 $OUT/bench_${TAG}.json
 echo "== bench ctx=2048 =="
-python bench.py --steps 100 --warmup 5 --ctx 2048 --no-cpu-baseline --phase-profile > $OUT/bench_${TAG}_ctx2048.json 2> $OUT/bench_${TAG}_ctx2048.err
-tail -c 1500 $OUT/bench_${TAG}_ctx2048.json; grep PHASES $OUT/bench_${TAG}_ctx2048.err
+python bench.py --steps 100 --warmup 5 --ctx 2048 --no-cpu-baseline > $OUT/bench_${TAG}_ctx2048.json 2> $OUT/bench_${TAG}_ctx2048.err
+tail -c 1500 $OUT/bench_${TAG}_ctx2048.json
 echo "== reference arm =="
 python bench.py --impl reference --steps 2 --warmup 0 > $OUT/bench_${TAG}_reference.json 2>&1
 tail -c 1200 $OUT/bench_${TAG}_reference.json

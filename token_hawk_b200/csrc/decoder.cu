@@ -34,8 +34,16 @@ constexpr int kNumSlots = 4;                          // measured on B200: 3 -> 
                                                       // traffic ahead of the latency-critical barrier / prologue loads)
 constexpr int kMathWarps = 8;
 constexpr int kMathThreads = kMathWarps * 32;
-constexpr int kMathBase = 32;                         // warp 0 = producer, warps 1..8 = math, warp 9 = epilogue
-constexpr int kThreads = kMathBase + kMathThreads + 32;
+// Three warpgroups: {warp 0 producer, warp 1 epilogue, warps 2-3 parked} | math warps 0-3 | math warps 4-7.  A 10-warp CTA
+// would cap every thread at 168 registers (three warps share one SM sub-partition); with whole warpgroups the service
+// group hands registers to the math groups (setmaxnreg: 56 vs 224 per thread, 56 + 2 * 224 <= 512 per sub-partition lane).
+constexpr int kMathBase = 128;
+constexpr int kThreads = kMathBase + kMathThreads;
+#ifdef THK_SVC_REGS
+constexpr int kServiceRegs = THK_SVC_REGS, kMathRegs = 256 - THK_SVC_REGS / 2 - 4;
+#else
+constexpr int kServiceRegs = 72, kMathRegs = 216;     // measured (svc/math -> ms/token): 40/232 2.81, 56/224 2.79, 72/216 2.69, 104/200 2.73, 136/184 2.79
+#endif
 constexpr int kRows = 8;                              // rows per row group (= per tile)
 constexpr int kMaxTilePos = 128;                      // attention: positions per tile cap
 constexpr int kMaxHeadDim = 128;
@@ -62,6 +70,13 @@ struct DecParams {
     const float* norm;
     const uint16_t* out_w;
     float *x, *h1, *q, *ff, *part;
+    // Flagged copies of h1 / ff / x for the barrier-free transitions Wo -> W13 -> W2 -> next QKV (single GPU): element
+    // = (epoch << 32) | f32 bits, written with ONE 64-bit store, so a reader that sees this layer's epoch sees the value.
+    unsigned long long *h1f, *fff, *xf;
+    unsigned flag_epoch;                // epoch of layer l in this launch = flag_epoch + l + 1
+    int dataflow;                       // 1: the three transitions above synchronise through the flagged vectors, no grid barrier
+    int nosync;                         // DEBUG (wrong results): skip every cross-CTA wait, to time the pipeline without synchronisation
+    int poll_single;                    // flagged reads: after a stale read spin on the one stale element before re-reading all
     float* amax_val;
     int* amax_idx;
     unsigned *bar_ctr, *bar_next;
@@ -153,6 +168,13 @@ __device__ __forceinline__ float lds32f(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void st_flagged(unsigned long long* p, float v, unsigned epoch) {
+    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void ld_flagged2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void st_release_sys(unsigned* ptr, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
@@ -174,6 +196,14 @@ __device__ __forceinline__ unsigned* xflags(const DecParams& p, int rank, int se
     return (unsigned*)(p.xchg[rank] + xchg_tail(p)) + (2 + set) * p.tp_size;
 }
 
+// The in-kernel timeline is compiled in only with -DTHK_PROFILE (token_hawk_b200/lib_prof): its marks must be out-of-line
+// calls (an inlined %globaltimer read is hoisted above barriers by ptxas), and ANY ABI call in the kernel makes ptxas
+// cap every thread at the service warpgroup's register budget instead of honouring setmaxnreg per branch.
+#ifdef THK_PROFILE
+#define PROF(p) ((p).prof)
+#else
+#define PROF(p) ((unsigned long long*)nullptr)
+#endif
 constexpr int kProfPhases = 256;
 constexpr int kProfTiles = 64;   // after the producer stats: [cta][kProfTiles] tile-retired times, then [cta][kProfTiles] tile-issued times
 enum ProfSlot { PROF_START = 0, PROF_PROLOGUE = 1, PROF_FIRST_TILE = 2, PROF_LAST_TILE = 3, PROF_ARRIVE = 4, PROF_PROD_LAST = 5, PROF_WAIT_FULL = 6, PROF_PROD_FIRST = 7 };
@@ -188,18 +218,18 @@ __device__ __noinline__ void prof_mark(unsigned long long* prof, unsigned phase,
 // an inlined %globaltimer read is hoisted by ptxas above barriers and waits (measured: phase starts recorded ~3 us
 // early), a call is a scheduling fence.
 __device__ __forceinline__ void mark(unsigned long long* pm, const DecParams& p, unsigned phase, int slot) {
-    if (pm != nullptr) prof_mark(p.prof, phase, slot);
+    if (pm != nullptr) prof_mark(PROF(p), phase, slot);
 }
 
 __device__ __forceinline__ bool aborted(const DecParams& p) { return ld_volatile_u32(p.status) != 0; }
-__device__ __noinline__ void raise_abort(const DecParams& p, unsigned code, unsigned a, unsigned b) {
+__device__ __forceinline__ void raise_abort(const DecParams& p, unsigned code, unsigned a, unsigned b) {
     if (atomicCAS(p.status, 0u, code) == 0u) { p.status[1] = a; p.status[2] = b; p.status[3] = blockIdx.x; }
 }
 
 // Slow path of every mbarrier wait: bounded by %globaltimer.  Returns false when the watchdog fired or
 // another CTA aborted; the caller then runs the rest of the (static) schedule without waiting, so the
 // kernel still terminates and the host sees THK_E_TIMEOUT instead of a wedged GPU.
-__device__ __noinline__ bool mbar_wait_slow(const DecParams& p, uint32_t bar, uint32_t parity, unsigned tag) {
+__device__ __forceinline__ bool mbar_wait_slow(const DecParams& p, uint32_t bar, uint32_t parity, unsigned tag) {
     const unsigned long long t0 = gtimer();
     unsigned it = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -219,13 +249,13 @@ struct SmemMisc {
     unsigned long long empty[kNumSlots];
     unsigned long long red_full[kDumpBufs];   // row-group sums `buf` written by all math warps
     unsigned long long red_free[kDumpBufs];   // ... and consumed by the epilogue warp
-    float norm_part[kMathWarps];
     float2 rope[kMaxHeadDim / 2];       // (cos, sin) of n_past * theta_i for this token
     int range[5][2];                    // this CTA's row range [r, r_end) of every matvec phase (computed once per launch)
 };
 constexpr int kMiscBytes = 1024;
 static_assert(sizeof(SmemMisc) <= kMiscBytes, "SmemMisc too large");
-constexpr int kRedFloats = kMathWarps * kRows;                 // one row-group hand-off: [warp][row] warp-level sums
+constexpr int kRecFloats = kRows + 1;                          // per warp: 8 row sums + its share of sum(v^2) of the phase input
+constexpr int kRedFloats = kMathWarps * kRecFloats;            // one row-group hand-off record
 constexpr int kAttScratchOff = kDumpBufs * kRedFloats;         // attention scratch (floats) behind the hand-off ring
 constexpr int kRedBytes = 8 * 1024;                            // ring (2 KB) + attention scratch (<= 6 KB)
 static_assert(kAttScratchOff * 4 + (kMathWarps * kMaxHeadDim + 2 * kMathWarps + 2 * kMaxHeadDim) * 4 <= kRedBytes, "attention scratch does not fit");
@@ -355,9 +385,9 @@ __device__ __forceinline__ void wait_empty(const DecParams& p, const Smem& S, Pr
     if (c.dead) return;
     const uint32_t bar = S.empty_a + c.ring.sl * 8;
     if (!mbar_try_wait(bar, c.ring.par ^ 1u)) {
-        const long long t0 = p.prof ? clock64() : 0;
+        const long long t0 = PROF(p) ? clock64() : 0;
         c.dead = !mbar_wait_slow(p, bar, c.ring.par ^ 1u, tag);
-        if (p.prof) c.wait_cyc += clock64() - t0;
+        if (PROF(p)) c.wait_cyc += clock64() - t0;
     }
 }
 
@@ -400,19 +430,19 @@ __device__ __forceinline__ void produce_mat_phase(const DecParams& p, const Smem
                     }
                 }
                 wait_empty(p, S, c, 1);
-                if (p.prof && first && lane == 0) { prof_mark(p.prof, phase_idx, PROF_PROD_FIRST); first = false; }
+                if (PROF(p) && first && lane == 0) { prof_mark(PROF(p), phase_idx, PROF_PROD_FIRST); first = false; }
                 const uint32_t fb = S.full_a + c.ring.sl * 8, dst = S.slots_a + c.ring.sl * kSlotBytes;
                 const uint32_t row_bytes = (uint32_t)ncols * 2u;
                 if (lane == 0) mbar_expect_tx(fb, (uint32_t)it.nrows * row_bytes);
                 __syncwarp();
                 if (lane < it.nrows) bulk_g2s(dst + (uint32_t)lane * row_bytes, wrow + (size_t)lane * C + col0, row_bytes, fb, c.pol);
-                if (p.prof && (int)phase_idx == p.prof_phase && j < kProfTiles && lane == 0) prof_tile(p.prof, 1, j);
+                if (PROF(p) && (int)phase_idx == p.prof_phase && j < kProfTiles && lane == 0) prof_tile(PROF(p), 1, j);
                 c.ring.advance();
                 ++c.tiles;
             }
         }
     }
-    if (p.prof && lane == 0) prof_mark(p.prof, phase_idx, PROF_PROD_LAST);
+    if (PROF(p) && lane == 0) prof_mark(PROF(p), phase_idx, PROF_PROD_LAST);
 }
 
 __device__ __forceinline__ void produce_att_phase(const DecParams& p, const Smem& S, Prod& c, const thk_llama_layer& L, unsigned phase_idx) {
@@ -430,7 +460,7 @@ __device__ __forceinline__ void produce_att_phase(const DecParams& p, const Smem
             const uint32_t bytes = (uint32_t)np * D * 4u;
             for (int kv = 0; kv < 2; ++kv) {
                 wait_empty(p, S, c, 2);
-                if (p.prof && first && lane == 0) { prof_mark(p.prof, phase_idx, PROF_PROD_FIRST); first = false; }
+                if (PROF(p) && first && lane == 0) { prof_mark(PROF(p), phase_idx, PROF_PROD_FIRST); first = false; }
                 const float* base = (kv == 0 ? L.key_cache : L.value_cache) + ((size_t)h * p.n_ctx + pos) * D;
                 const uint32_t fb = S.full_a + c.ring.sl * 8;
                 if (lane == 0) { mbar_expect_tx(fb, bytes); bulk_g2s(S.slots_a + c.ring.sl * kSlotBytes, base, bytes, fb, c.pol); }
@@ -440,7 +470,7 @@ __device__ __forceinline__ void produce_att_phase(const DecParams& p, const Smem
             }
         }
     }
-    if (p.prof && lane == 0) prof_mark(p.prof, phase_idx, PROF_PROD_LAST);
+    if (PROF(p) && lane == 0) prof_mark(PROF(p), phase_idx, PROF_PROD_LAST);
 }
 
 __device__ __forceinline__ int phase_of(int k) { return k == K_QKV ? PH_QKV : k == K_WO ? PH_WO : k == K_W13 ? PH_W13 : k == K_W2 ? PH_W2 : PH_OUT; }
@@ -462,8 +492,8 @@ __device__ void producer_main(const DecParams& p, const Smem& S) {
         }
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
     }
-    if (p.prof && (threadIdx.x & 31) == 0) {
-        unsigned long long* stt = p.prof + (size_t)gridDim.x * kProfPhases * 8 + (size_t)blockIdx.x * 4;
+    if (PROF(p) && (threadIdx.x & 31) == 0) {
+        unsigned long long* stt = PROF(p) + (size_t)gridDim.x * kProfPhases * 8 + (size_t)blockIdx.x * 4;
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         stt[0] = (unsigned long long)c.wait_cyc; stt[1] = (unsigned long long)(clock64() - t0); stt[2] = c.tiles; stt[3] = smid;
@@ -497,21 +527,42 @@ __device__ __forceinline__ void fma8(const uint4& w, const unsigned long long (&
 }
 
 
+// One tile's operands in registers: 8 rows x this lane's 8 columns of f16 weights, and the matching activations packed
+// for FFMA2.
+struct TileRegs {
+    uint4 w[kRows];
+    unsigned long long xp[4];
+};
+// issue the ten 128-bit shared loads of the tile in ring slot `sl` (columns [col0, col0 + ncols) of the phase input)
+__device__ __forceinline__ void tile_load(const Smem& S, uint32_t sl, uint32_t xlane_a, int col, int lane, int col0, int ncols, TileRegs& t) {
+    const bool ok = col < ncols;                               // lanes past a short tile's last column read column 0 against zeros
+    const uint32_t stride = (uint32_t)ncols * 2u;
+    const uint32_t xa = ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4);
+    const uint32_t wa = S.slots_a + sl * kSlotBytes + (ok ? (uint32_t)col << 1 : 0u);
+    float4 x0 = lds128f(xa), x1 = lds128f(xa + 512u);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) t.w[r] = lds128(wa + (uint32_t)r * stride);
+    if (!ok) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
+    t.xp[0] = pack2(x0.x, x0.y); t.xp[1] = pack2(x0.z, x0.w); t.xp[2] = pack2(x1.x, x1.y); t.xp[3] = pack2(x1.z, x1.w);
+}
+
 // Stream this CTA's tiles of one matvec phase.  Per tile a warp owns one 256-column chunk of all 8 rows
 // (rows past a short group's end hold stale bytes; their sums are never read).  `gq` counts the row
-// groups handed to the epilogue warp since kernel start (dump buffer = gq & 1, use = gq >> 1).
+// groups handed to the epilogue warp since kernel start (hand-off record = gq % kDumpBufs).
 //
-// The per-tile body is the consumer's critical path: when a phase starts the ring is full and HBM idles until slots
-// come back, so the faster a tile is retired the shorter every phase boundary.  Hence: all ten 128-bit loads of a
-// tile are issued up front by shared-window address, the body is branch free (lanes past a short tile's last column
-// read column 0 against a zero activation), the math is packed FFMA2, and nothing but the ring bookkeeping remains.
-__device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S, Cons& c, int ph, unsigned& gq,
+// The per-tile body is the consumer's critical path: HBM delivers a 32 KB tile per ~0.62 us and SM, and only a consumer
+// that retires READY tiles faster than that turns the tiles buffered during a phase boundary into saved time.  Hence:
+// all ten 128-bit loads of a tile issued up front by shared-window address, a branch-free body (lanes past a short
+// tile's last column read column 0 against a zero activation), packed FFMA2, and nothing but ring bookkeeping around
+// it.  (Software pipelining across tiles -- the next tile's loads before this tile's math, second register set -- was
+// built and dropped: ptxas spilled the tile registers inside the loop and the kernel ran 2.8x slower.)
+__device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S, Cons& c, int ph, unsigned& gq, float ss,
                                                int cw, int lane, unsigned phase_idx, unsigned long long* pm) {
     const PhaseDesc& d = p.ph[ph];
     const int C = d.C, KT = d.KT, CT = d.CT, nsub = d.paired ? 2 : 1;
     const int col = (cw << 8) + (lane << 3);                                  // this lane's first column inside a tile
     const uint32_t xlane_a = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);   // + col0 * 4: first float4; second 512 B on
-    const uint32_t dump_a = S.red_a + (uint32_t)(cw * kRows * 4);                 // this warp's [row] record inside a hand-off buffer
+    const uint32_t dump_a = S.red_a + (uint32_t)(cw * kRecFloats * 4);            // this warp's record inside a hand-off buffer
     bool first = pm != nullptr;
     int ntile = 0;
     RowIt it;
@@ -524,23 +575,14 @@ __device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S
             for (int r = 0; r < kRows; ++r) acc[r] = 0ull;
             int col0 = 0;
             for (int kt = 0; kt < KT; ++kt, col0 += CT) {
-                const int ncols = min(CT, C - col0);
-                const bool ok = col < ncols;
-                const uint32_t stride = (uint32_t)ncols * 2u;
-                const uint32_t xa = ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4);
+                TileRegs t;
                 wait_full(p, S, c, 3);
                 if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
-                const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (ok ? (uint32_t)col << 1 : 0u);
-                float4 x0 = lds128f(xa), x1 = lds128f(xa + 512u);
-                uint4 w[kRows];
+                tile_load(S, c.ring.sl, xlane_a, col, lane, col0, min(CT, C - col0), t);
 #pragma unroll
-                for (int r = 0; r < kRows; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
-                if (!ok) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
-                const unsigned long long xp[4] = {pack2(x0.x, x0.y), pack2(x0.z, x0.w), pack2(x1.x, x1.y), pack2(x1.z, x1.w)};
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) fma8(w[r], xp, acc[r]);
+                for (int r = 0; r < kRows; ++r) fma8(t.w[r], t.xp, acc[r]);
                 release_slot(S, c, lane);
-                if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(p.prof, 0, ntile++);
+                if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
             }
             // Hand the row sums to the epilogue warp.  A transposing shuffle reduction (4 + 2 + 1 exchanges halve the rows
             // a lane holds while doubling the lanes summed, then 2 plain steps) leaves the warp total of row (lane >> 2) & 7
@@ -577,6 +619,7 @@ __device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S
                 if (!mbar_try_wait(fb, (use - 1) & 1u)) c.dead = !mbar_wait_slow(p, fb, (use - 1) & 1u, 6);
             }
             if ((lane & 3) == 0) sts32f(dump_a + (buf * kRedFloats + (unsigned)((lane >> 2) & 7)) * 4u, v[0]);
+            if (lane == 1) sts32f(dump_a + (buf * kRedFloats + kRows) * 4u, ss);      // this warp's share of sum(v^2) (norm phases)
             __syncwarp();
             if (lane == 0) mbar_arrive(S.red_full_a + buf * 8);
             ++gq;
@@ -589,6 +632,53 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     float s = a.x * b.x;
     s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
     return s;
+}
+
+// Flagged-vector read: this lane's 8 columns of NCH chunks (chunk u starts at element col[u]; col[u] < 0: no such chunk),
+// all loads in flight together, repeated until every element carries `epoch` -- that IS the synchronisation with the
+// CTAs that produce the vector (no grid barrier on these transitions).  After a stale read the lane first spins on the one
+// stale element (8 bytes per round instead of 64 * NCH), then reads everything again.  Bounded by the watchdog.
+template <int NCH>
+__device__ __forceinline__ void load_flagged(const DecParams& p, const unsigned long long* vec, const int (&col)[NCH], unsigned epoch,
+                                             unsigned long long (&e)[NCH * 8], bool& dead) {
+    unsigned long long t0 = 0;
+    unsigned it = 0;
+    while (true) {
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+            if (col[u] >= 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ld_flagged2(vec + col[u] + 2 * j, e[u * 8 + 2 * j], e[u * 8 + 2 * j + 1]);
+            }
+        }
+        int stale = -1;
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+            if (col[u] >= 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if ((unsigned)(e[u * 8 + j] >> 32) != epoch && stale < 0) stale = col[u] + j;
+            }
+        }
+        if (stale < 0 || dead || p.nosync) break;
+        if (p.poll_single) {
+            unsigned long long w;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(vec + stale) : "memory");
+                if ((++it & 63u) == 0u) {
+                    if (t0 == 0) t0 = gtimer();
+                    if (aborted(p)) { dead = true; break; }
+                    if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x500u, (unsigned)stale, epoch); dead = true; break; }
+                }
+            } while ((unsigned)(w >> 32) != epoch);
+        } else if ((++it & 63u) == 0u) {
+            if (t0 == 0) t0 = gtimer();
+            if (aborted(p)) dead = true;
+            else if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x500u, (unsigned)stale, epoch); dead = true; }
+        }
+    }
+}
+__device__ __forceinline__ float4 flagged_f4(const unsigned long long* e) {
+    return make_float4(__uint_as_float((unsigned)e[0]), __uint_as_float((unsigned)e[1]), __uint_as_float((unsigned)e[2]), __uint_as_float((unsigned)e[3]));
 }
 
 // Single-query attention over this CTA's (head, KV split) units (cmdbuf_mat_mul QK^T * 1/sqrt(D),
@@ -739,73 +829,97 @@ __device__ __forceinline__ void sts128f(uint32_t a, const float4& v) {
 // xs <- v * gain, v = the residual stream (cmdbuf_rms_norm + cmdbuf_row_element_multiply, th.cpp:1153-1200,1298-1315; under
 // tensor parallelism the residual adds of th-llama.cpp:409/447 move here).  The RMS scale 1/sqrt(mean(v^2) + 1e-6) is a
 // scalar, so it is applied to the finished row sums by the epilogue warp instead: here every warp only leaves its share
-// of sum(v^2) in norm_part[cw].  When `out` is given, v is also written back as the new residual stream, each float4 by
-// exactly one CTA.  The gain was L2-prefetched before the grid barrier.
-__device__ __forceinline__ void prologue_norm(const DecParams& p, const Smem& S, const PhaseDesc& d, const float* src, const uint16_t* emb_row,
-                                              const float* gain, int which, float* out, int cw, int lane) {
+// of sum(v^2) (returned; it travels to the epilogue warp inside every hand-off record).  When `out` is given, v is also written back as the new residual stream, each float4
+// by exactly one CTA.  `fsrc` != nullptr: v comes from a flagged vector (waits for `epoch`), else from src / the embedding
+// row (after a grid barrier).  The gain was L2-prefetched during the previous phase.
+__device__ __forceinline__ float prologue_norm(const DecParams& p, const Smem& S, const PhaseDesc& d, const float* src, const uint16_t* emb_row,
+                                               const unsigned long long* fsrc, unsigned epoch, const float* gain, int which, float* out,
+                                               int cw, int lane, bool& dead) {
     const int n = d.C;
     const int lcol = (cw << 8) + (lane << 3);                 // this lane's first column inside a K tile
     const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
     float ss = 0.f;
-    for (int kt0 = 0; kt0 < d.KT; kt0 += 2) {                 // two K tiles (4 + 4 float4 loads) per L2 round trip
+    for (int kt0 = 0; kt0 < d.KT; kt0 += 2) {                 // two K tiles per L2 round trip
         float4 v[4], g[4];
+        int col[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int c = (kt0 + u) * d.CT + lcol;
-            if (kt0 + u < d.KT && lcol < d.CT && c < n) {
-                v[2 * u] = load_summed(p, src, emb_row, which, c);
-                v[2 * u + 1] = load_summed(p, src, emb_row, which, c + 4);
+            col[u] = (kt0 + u < d.KT && lcol < d.CT && c < n) ? c : -1;
+            if (col[u] >= 0) {
                 g[2 * u] = __ldg((const float4*)(gain + c));
                 g[2 * u + 1] = __ldg((const float4*)(gain + c + 4));
             }
         }
+        if (fsrc != nullptr) {
+            unsigned long long e[16];
+            load_flagged<2>(p, fsrc, col, epoch, e, dead);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) if (col[u] >= 0) { v[2 * u] = flagged_f4(e + 8 * u); v[2 * u + 1] = flagged_f4(e + 8 * u + 4); }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) if (col[u] >= 0) {
+                v[2 * u] = load_summed(p, src, emb_row, which, col[u]);
+                v[2 * u + 1] = load_summed(p, src, emb_row, which, col[u] + 4);
+            }
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const int c = (kt0 + u) * d.CT + lcol;
-            if (kt0 + u < d.KT && lcol < d.CT && c < n) {
+            if (col[u] >= 0) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const float4 t = v[2 * u + hh], gg = g[2 * u + hh];
                     ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
-                    const int i = c + 4 * hh;
+                    const int i = col[u] + 4 * hh;
                     if (out && (unsigned)(i >> 2) % gridDim.x == blockIdx.x) *(float4*)(out + i) = t;
                     sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2) + 512u * hh, make_float4(t.x * gg.x, t.y * gg.y, t.z * gg.z, t.w * gg.w));
                 }
             }
         }
     }
-    ss = warp_sum(ss);
-    if (lane == 0) S.misc->norm_part[cw] = ss;
+    return warp_sum(ss);
 }
-// xs <- src (the FFN hidden vector for W2)
-__device__ __forceinline__ void prologue_copy(const Smem& S, const PhaseDesc& d, const float* src, int cw, int lane) {
+// xs <- src (the FFN hidden vector for W2); fsrc != nullptr: from the flagged vector, waiting for `epoch`
+__device__ __forceinline__ void prologue_copy(const DecParams& p, const Smem& S, const PhaseDesc& d, const float* src, const unsigned long long* fsrc,
+                                              unsigned epoch, int cw, int lane, bool& dead) {
     const int n = d.C;
     const int lcol = (cw << 8) + (lane << 3);
     const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
-    for (int kt0 = 0; kt0 < d.KT; kt0 += 3) {                 // three K tiles (6 float4 loads) per L2 round trip
+    for (int kt0 = 0; kt0 < d.KT; kt0 += 3) {                 // three K tiles per L2 round trip
         float4 v[6];
+        int col[3];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             const int c = (kt0 + u) * d.CT + lcol;
-            if (kt0 + u < d.KT && lcol < d.CT && c < n) {
-                v[2 * u] = __ldcg((const float4*)(src + c));
-                v[2 * u + 1] = __ldcg((const float4*)(src + c + 4));
+            col[u] = (kt0 + u < d.KT && lcol < d.CT && c < n) ? c : -1;
+        }
+        if (fsrc != nullptr) {
+            unsigned long long e[24];
+            load_flagged<3>(p, fsrc, col, epoch, e, dead);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) if (col[u] >= 0) { v[2 * u] = flagged_f4(e + 8 * u); v[2 * u + 1] = flagged_f4(e + 8 * u + 4); }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) if (col[u] >= 0) {
+                v[2 * u] = __ldcg((const float4*)(src + col[u]));
+                v[2 * u + 1] = __ldcg((const float4*)(src + col[u] + 4));
             }
         }
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-            const int c = (kt0 + u) * d.CT + lcol;
-            if (kt0 + u < d.KT && lcol < d.CT && c < n) {
+            if (col[u] >= 0) {
                 sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2), v[2 * u]);
                 sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2) + 512u, v[2 * u + 1]);
             }
         }
     }
 }
-// xs <- attention output of the local heads: merge the KV splits of every head (softmax denominators included).  One
-// float4 x <= 4 splits per round (loads in flight together; ~0.6 us per L2 round trip under the weight stream): the
-// kernel sits at the 168-register ceiling of a 10-warp CTA (three warps share one SM sub-partition) and wider rounds
-// measurably slow the whole kernel down (spilled phase-loop state; measured 2.83 -> 2.92 ms/token).
+// xs <- attention output of the local heads: merge the KV splits of every head (softmax denominators included).  A lane
+// merges the two float4 of one chunk per round (they lie in the same head, so they share {m, l}); the loads of a round are
+// in flight together (~0.6 us per L2 round trip under the weight stream).  (A flagged, barrier-free version of the
+// QKV -> attention -> Wo hand-overs was built and measured slower: 2.69 -> 2.96 ms/token -- the polling of 128 split
+// records by every CTA costs more than the two grid barriers it removes.)
+#ifdef THK_MERGE1
 __device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Smem& S, const PhaseDesc& d, int cw, int lane) {
     const AttSched a = make_att(p);
     const int D = p.head_dim, ps = part_stride(p);
@@ -847,6 +961,52 @@ __device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Sme
         sts128f(xa + (uint32_t)((kt * d.CT) << 2) + 512u * hh, o);
     }
 }
+#else
+__device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Smem& S, const PhaseDesc& d, int cw, int lane) {
+    const AttSched a = make_att(p);
+    const int D = p.head_dim, ps = part_stride(p);
+    const int lcol = (cw << 8) + (lane << 3);
+    const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
+    for (int kt = 0; kt < d.KT; ++kt) {
+        const int c = kt * d.CT + lcol;
+        if (lcol >= d.CT || c >= d.C) continue;
+        const int h = c / D, dd = c - h * D;                  // 8 consecutive columns never straddle a head (D % 8 == 0)
+        const size_t pbase = (size_t)h * a.S * ps;
+        float M = -INFINITY, lt = 0.f;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        for (int s0 = 0; s0 < a.S; s0 += 4) {
+            float2 ml[4];
+            float4 v0[4], v1[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (s0 + t < a.S) {
+                const float* r = p.part + pbase + (size_t)(s0 + t) * ps;
+                ml[t] = __ldcg((const float2*)r);
+                v0[t] = __ldcg((const float4*)(r + 4 + dd));
+                v1[t] = __ldcg((const float4*)(r + 8 + dd));
+            }
+            float Mn = M;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (s0 + t < a.S) Mn = fmaxf(Mn, ml[t].x);
+            const float c0 = expf(M - Mn);                   // first round: exp(-inf) = 0
+            lt *= c0;
+            o0.x *= c0; o0.y *= c0; o0.z *= c0; o0.w *= c0;
+            o1.x *= c0; o1.y *= c0; o1.z *= c0; o1.w *= c0;
+            M = Mn;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (s0 + t < a.S) {
+                const float e = expf(ml[t].x - M);
+                lt = fmaf(ml[t].y, e, lt);
+                o0.x = fmaf(v0[t].x, e, o0.x); o0.y = fmaf(v0[t].y, e, o0.y); o0.z = fmaf(v0[t].z, e, o0.z); o0.w = fmaf(v0[t].w, e, o0.w);
+                o1.x = fmaf(v1[t].x, e, o1.x); o1.y = fmaf(v1[t].y, e, o1.y); o1.z = fmaf(v1[t].z, e, o1.z); o1.w = fmaf(v1[t].w, e, o1.w);
+            }
+        }
+        o0.x /= lt; o0.y /= lt; o0.z /= lt; o0.w /= lt;
+        o1.x /= lt; o1.y /= lt; o1.z /= lt; o1.w /= lt;
+        sts128f(xa + (uint32_t)((kt * d.CT) << 2), o0);
+        sts128f(xa + (uint32_t)((kt * d.CT) << 2) + 512u, o1);
+    }
+}
+#endif
 
 __device__ __forceinline__ void prefetch_gain(const float* gain, int n, int ct) {
     for (int off = ct * 32; off < n; off += kMathThreads * 32)       // one 128-byte line per thread
@@ -855,7 +1015,7 @@ __device__ __forceinline__ void prefetch_gain(const float* gain, int n, int ct) 
 
 __device__ void math_main(const DecParams& p, const Smem& S) {
     const int ct = (int)threadIdx.x - kMathBase, cw = ct >> 5, lane = ct & 31;
-    unsigned long long* const pm = (p.prof != nullptr && ct == 0) ? p.prof + (size_t)blockIdx.x * kProfPhases * 8 : nullptr;
+    unsigned long long* const pm = (PROF(p) != nullptr && ct == 0) ? PROF(p) + (size_t)blockIdx.x * kProfPhases * 8 : nullptr;
     Cons c{{0u, 0u}, false};
     unsigned gq = 0;
     int tok = *p.token;
@@ -866,34 +1026,39 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
     const int nsteps = 5 * p.n_layer + 1;
     const bool tp = p.tp_size > 1;
     int l = 0, k = K_QKV;
+    float ss = 0.f;                       // this warp's share of sum(v^2) of the current norm phase's input
     for (int i = 0; i < nsteps; ++i) {
         const thk_llama_layer* L = p.layers + (l < p.n_layer ? l : p.n_layer - 1);
         // ---- prologue ----
+        const unsigned epoch = p.flag_epoch + (unsigned)l + 1u;          // flagged vectors written in layer l (K_QKV / K_OUT read layer l-1's x)
         if (k == K_QKV || k == K_W13 || k == K_OUT) {
             const float* gain = (k == K_QKV) ? L->attention_norm : (k == K_W13) ? L->ffn_norm : p.norm;
             // step 0: x <- f32(tok_embeddings[token]) (th-llama.cpp:577-585; device-side like :552-575): every CTA
             // converts the row itself and one copy goes to p.x for the Wo residual.  Under tensor parallelism the
             // W13 / QKV prologues also finish the all-reduce: h1 = x + sum of Wo partials, x = h1 + sum of W2 partials.
             const float* src = i == 0 ? nullptr : (k == K_W13) ? (tp ? p.x : p.h1) : (tp ? p.h1 : p.x);
+            const unsigned long long* fsrc = (i == 0 || !p.dataflow) ? nullptr : (k == K_W13 ? p.h1f : p.xf);
             const int which = (i == 0 || !tp) ? -1 : (k == K_W13 ? 0 : 1);
             float* out = i == 0 ? p.x : !tp ? nullptr : (k == K_W13 ? p.h1 : p.x);
-            prologue_norm(p, S, p.ph[phase_of(k)], src, emb_row, gain, which, out, cw, lane);
+            ss = prologue_norm(p, S, p.ph[phase_of(k)], src, emb_row, fsrc, k == K_W13 ? epoch : epoch - 1u, gain, which, out, cw, lane, c.dead);
         } else if (k == K_WO) {
             prologue_att_merge(p, S, p.ph[PH_WO], cw, lane);
         } else if (k == K_W2) {
-            prologue_copy(S, p.ph[PH_W2], p.ff, cw, lane);
+            prologue_copy(p, S, p.ph[PH_W2], p.ff, p.dataflow ? p.fff : nullptr, epoch, cw, lane, c.dead);
         }
         mark(pm, p, (unsigned)i, PROF_PROLOGUE);
         // ---- tiles ----
         if (k == K_ATT) math_att_phase(p, S, c, *L, ct, cw, lane);
-        else math_mat_phase(p, S, c, phase_of(k), gq, cw, lane, (unsigned)i, pm);
+        else math_mat_phase(p, S, c, phase_of(k), gq, ss, cw, lane, (unsigned)i, pm);
         if (k == K_OUT) break;
         // ---- next phase's gain while the grid barrier forms ----
         if (k == K_WO) prefetch_gain(L->ffn_norm, p.n_embd, ct);
         else if (k == K_W2) prefetch_gain(l + 1 < p.n_layer ? p.layers[l + 1].attention_norm : p.norm, p.n_embd, ct);
         mark(pm, p, (unsigned)i, PROF_ARRIVE);
-        if (k == K_ATT) bar_sync(BAR_PRE, kMathThreads + 32);    // our global writes (split results) precede the epilogue warp's arrive
-        bar_sync(BAR_ALL, kMathThreads + 32);                     // the epilogue warp has passed the grid barrier
+        if (!(p.dataflow && (k == K_WO || k == K_W13 || k == K_W2))) {   // else: the next prologue waits on the flagged vector itself
+            if (k == K_ATT) bar_sync(BAR_PRE, kMathThreads + 32);    // our global writes (split results) precede the epilogue warp's arrive
+            bar_sync(BAR_ALL, kMathThreads + 32);                     // the epilogue warp has passed the grid barrier
+        }
         mark(pm, p, (unsigned)i + 1, PROF_START);
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
     }
@@ -909,7 +1074,7 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
 __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, int lane, bool& dead, int xset = -1, unsigned epoch = 0u) {
     if (xset >= 0) __threadfence_system();      // this warp's pushes to the peers are visible system-wide
     __syncwarp();
-    if (lane == 0 && !dead) {
+    if (lane == 0 && !dead && !p.nosync) {
         unsigned* const ctr = p.bar_ctr;
         red_release_add(ctr, 1u);
         const unsigned target = nbar * gridDim.x;
@@ -949,13 +1114,13 @@ __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, 
 enum EpiKind { EPI_QKV, EPI_WO, EPI_W13, EPI_W2, EPI_OUT };
 struct EpiState { float gate; float best; int best_idx; };
 
-__device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S, int ph, int kind, const thk_llama_layer* L,
+__device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S, int ph, int kind, const thk_llama_layer* L, unsigned epoch,
                                               EpiState& es, unsigned& gq, bool& dead, int lane) {
     const PhaseDesc& d = p.ph[ph];
     const int D = p.head_dim, tp_size = p.tp_size, tp_rank = p.tp_rank, n_ctx = p.n_ctx, n_past = p.n_past;
     const int nsub = d.paired ? 2 : 1;
     const int rr = lane & 7, qq = lane >> 3;          // this lane adds row rr of math warps 2 qq and 2 qq + 1
-    const uint32_t my_a = S.red_a + (uint32_t)((2 * qq * kRows + rr) * 4);
+    const uint32_t my_a = S.red_a + (uint32_t)((2 * qq * kRecFloats + rr) * 4);
     const bool has_resid = (kind == EPI_WO || kind == EPI_W2) && tp_size == 1;
     const bool need_scale = (kind == EPI_QKV || kind == EPI_W13 || kind == EPI_OUT);
     bool have_scale = false;
@@ -980,24 +1145,22 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
                 if (!mbar_try_wait(fb, use & 1u)) dead = !mbar_wait_slow(p, fb, use & 1u, 7);
             }
             const uint32_t src = my_a + buf * (uint32_t)(kRedFloats * 4);
-            float y = lds32f(src) + lds32f(src + kRows * 4);
+            float y = lds32f(src) + lds32f(src + kRecFloats * 4);
             y += __shfl_xor_sync(0xffffffffu, y, 8);
             y += __shfl_xor_sync(0xffffffffu, y, 16);      // every lane: total of row (lane & 7)
+            if (need_scale && !have_scale) {
+                // RMSNorm scale of this phase's input (th.cpp:1153-1200): every hand-off record carries the eight warps' shares
+                // of sum(v^2); added in warp order: deterministic.
+                float tot = 0.f;
+#pragma unroll
+                for (int w = 0; w < kMathWarps; ++w) tot += lds32f(S.red_a + (buf * kRedFloats + w * kRecFloats + kRows) * 4u);
+                scale = 1.0f / sqrtf(tot / (float)d.C + 1e-6f);
+                have_scale = true;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(S.red_free_a + buf * 8);
             ++gq;
-            if (need_scale) {
-                // RMSNorm scale of this phase's input (th.cpp:1153-1200): every math warp left its share of sum(v^2) before its
-                // first hand-off, so the eight parts are complete once any row group is.  Fixed order: deterministic.
-                if (!have_scale) {
-                    float tot = 0.f;
-#pragma unroll
-                    for (int w = 0; w < kMathWarps; ++w) tot += S.misc->norm_part[w];
-                    scale = 1.0f / sqrtf(tot / (float)d.C + 1e-6f);
-                    have_scale = true;
-                }
-                y *= scale;
-            }
+            if (need_scale) y *= scale;
             const float y1 = __shfl_down_sync(0xffffffffu, y, 1);     // the pair partner for RoPE
             if (lane < nrows) {
                 const int r = row0 + lane;
@@ -1013,15 +1176,19 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
                     }
                     break;
                 case EPI_WO:                                                           // th-llama.cpp:409
-                    if (tp_size == 1) p.h1[r] = resid + y;
+                    if (tp_size == 1) { const float v = resid + y; p.h1[r] = v; if (p.dataflow) st_flagged(p.h1f + r, v, epoch); }
                     else for (int dst = 0; dst < tp_size; ++dst) xb_ptr(p, dst, 0, tp_rank)[r] = y;   // partial -> every rank
                     break;
                 case EPI_W13:
                     if (sub == 0) es.gate = y;
-                    else { const float gv = es.gate; p.ff[r] = (gv / (1.0f + expf(-gv))) * y; }   // :436,:438
+                    else {                                                              // :436,:438
+                        const float gv = es.gate, v = (gv / (1.0f + expf(-gv))) * y;
+                        p.ff[r] = v;
+                        if (p.dataflow) st_flagged(p.fff + r, v, epoch);
+                    }
                     break;
                 case EPI_W2:                                                           // th-llama.cpp:447
-                    if (tp_size == 1) p.x[r] = resid + y;
+                    if (tp_size == 1) { const float v = resid + y; p.x[r] = v; if (p.dataflow) st_flagged(p.xf + r, v, epoch); }
                     else for (int dst = 0; dst < tp_size; ++dst) xb_ptr(p, dst, 1, tp_rank)[r] = y;
                     break;
                 default: {                                                             // EPI_OUT
@@ -1053,15 +1220,17 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
     for (int i = 0; i < nsteps; ++i) {
         if (k != K_ATT) {
             const int kind = k == K_QKV ? EPI_QKV : k == K_WO ? EPI_WO : k == K_W13 ? EPI_W13 : k == K_W2 ? EPI_W2 : EPI_OUT;
-            epi_mat_phase(p, S, phase_of(k), kind, k == K_OUT ? nullptr : p.layers + l, es, gq, dead, lane);
+            epi_mat_phase(p, S, phase_of(k), kind, k == K_OUT ? nullptr : p.layers + l, p.flag_epoch + (unsigned)l + 1u, es, gq, dead, lane);
         } else {
             bar_sync(BAR_PRE, kMathThreads + 32);
         }
         if (k == K_OUT) break;
-        ++nbar;
-        if (p.tp_size > 1 && (k == K_WO || k == K_W2)) { ++xk; grid_barrier(p, nbar, lane, dead, k == K_WO ? 0 : 1, p.epoch_base + xk); }
-        else grid_barrier(p, nbar, lane, dead);
-        bar_sync(BAR_ALL, kMathThreads + 32);
+        if (!(p.dataflow && (k == K_WO || k == K_W13 || k == K_W2))) {
+            ++nbar;
+            if (p.tp_size > 1 && (k == K_WO || k == K_W2)) { ++xk; grid_barrier(p, nbar, lane, dead, k == K_WO ? 0 : 1, p.epoch_base + xk); }
+            else grid_barrier(p, nbar, lane, dead);
+            bar_sync(BAR_ALL, kMathThreads + 32);
+        }
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
     }
     if (p.next_token || p.next_logit) {
@@ -1125,7 +1294,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
             }
         }
     }
-    if (p.prof && lane == 0) prof_mark(p.prof, 5u * (unsigned)p.n_layer + 1u, PROF_START);
+    if (PROF(p) && lane == 0) prof_mark(PROF(p), 5u * (unsigned)p.n_layer + 1u, PROF_START);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_constant__ DecParams p) {
@@ -1141,14 +1310,19 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 69) {
+    if (threadIdx.x >= 64 && threadIdx.x < 69) {            // (a parked warp of the service group)
         const int ph = (int)threadIdx.x - 64;
         RowIt::share(p.ph[ph], S.misc->range[ph][0], S.misc->range[ph][1]);
     }
     __syncthreads();
-    if (threadIdx.x < 32) producer_main(p, S);
-    else if (threadIdx.x < kMathBase + kMathThreads) math_main(p, S);
-    else epi_main(p, S);
+    if (threadIdx.x < kMathBase) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
+        if (threadIdx.x < 32) producer_main(p, S);
+        else if (threadIdx.x < 64) epi_main(p, S);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMathRegs));
+        math_main(p, S);
+    }
 }
 
 size_t decode_smem_bytes(int max_vec) {
@@ -1175,6 +1349,8 @@ struct thk_decoder {
     DecParams p{};
     thk_llama_layer* d_layers = nullptr;
     float* scratch = nullptr;
+    unsigned long long* flagged = nullptr;   // h1f [n_embd] | xf [n_embd] | fff [Fh]
+    unsigned flag_seq = 0;
     unsigned* ctrl = nullptr;       // [64 barrier counters][4 status]
     int* d_tok = nullptr;           // chained-token scratch for generate
     unsigned launch_seq = 0;
@@ -1263,6 +1439,12 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     float* f = d->scratch;
     p.x = f; f += p.n_embd; p.h1 = f; f += p.n_embd; p.q = f; f += p.Eh;
     p.ff = f; f += (p.Fh + 3) & ~3; p.part = f; f += part_n; p.amax_val = f; f += d->grid; p.amax_idx = (int*)f;
+    const size_t nflag = (size_t)2 * p.n_embd + (size_t)((p.Fh + 1) & ~1);
+    THK_CUDA(cudaMalloc(&d->flagged, nflag * sizeof(unsigned long long)));
+    THK_CUDA(cudaMemset(d->flagged, 0, nflag * sizeof(unsigned long long)));     // epoch 0 is never used
+    p.h1f = d->flagged; p.xf = p.h1f + p.n_embd; p.fff = p.xf + p.n_embd;
+    p.dataflow = (tp == 1 && p.n_layer <= 254 && !(getenv("THK_DATAFLOW") && atoi(getenv("THK_DATAFLOW")) == 0)) ? 1 : 0;
+    p.poll_single = getenv("THK_POLL_SINGLE") ? atoi(getenv("THK_POLL_SINGLE")) : 1;
     const size_t nctrl = 64 + 4;
     THK_CUDA(cudaMalloc(&d->ctrl, nctrl * sizeof(unsigned)));
     THK_CUDA(cudaMemset(d->ctrl, 0, nctrl * sizeof(unsigned)));
@@ -1283,7 +1465,7 @@ extern "C" int thk_decoder_destroy(thk_decoder* d) {
     if (!d) return THK_OK;
     cudaSetDevice(d->ctx->device);
     cudaStreamSynchronize(d->ctx->stream);
-    cudaFree(d->d_layers); cudaFree(d->scratch); cudaFree(d->ctrl); cudaFree(d->d_tok); cudaFree(d->d_prof); cudaFree(d->xchg);
+    cudaFree(d->d_layers); cudaFree(d->scratch); cudaFree(d->flagged); cudaFree(d->ctrl); cudaFree(d->d_tok); cudaFree(d->d_prof); cudaFree(d->xchg);
     delete d;
     return THK_OK;
 }
@@ -1297,6 +1479,7 @@ static int launch_step(thk_decoder* d, const int32_t* token, int32_t n_past, flo
         p.epoch_base = d->epoch;
         d->epoch += 2u * (unsigned)p.n_layer + 2u;
     }
+    p.flag_epoch = (++d->flag_seq) << 8;                 // layer l of this launch stamps its vectors with flag_epoch + l + 1
     p.bar_ctr = d->ctrl + (d->launch_seq % 64);
     p.bar_next = d->ctrl + ((d->launch_seq + 1) % 64);
     ++d->launch_seq;
@@ -1339,6 +1522,9 @@ extern "C" int thk_decoder_generate(thk_decoder* d, const int32_t* first_token, 
 // 8 u64 slots of %globaltimer ns (ProfSlot), followed by per-CTA producer stats [empty-wait cycles, total cycles, tiles, smid]
 extern "C" int thk_decoder_profile(thk_decoder* d, int enable, unsigned long long* host_out, int n) {
     THK_CHECK_ARG(d, "thk_decoder_profile: null argument");
+#ifndef THK_PROFILE
+    if (enable) { thk_set_error("thk_decoder_profile: this library was built without -DTHK_PROFILE (load token_hawk_b200/lib_prof: THK_LIBDIR=lib_prof)"); return THK_E_UNSUPPORTED; }
+#endif
     THK_ENTER(d->ctx);
     if (enable && !d->d_prof) {
         const size_t nprof = (size_t)d->grid * (kProfPhases * 8 + 4 + 2 * kProfTiles);
@@ -1358,6 +1544,9 @@ extern "C" int thk_decoder_tune(thk_decoder* d, const char* key, int value) {
     THK_CHECK_ARG(d && key, "thk_decoder_tune: null argument");
     if (!strcmp(key, "l2_ahead_kb")) { THK_CHECK_ARG(value >= 0 && value <= 1024, "l2_ahead_kb out of range"); d->p.l2_ahead = (unsigned)value * 1024u; }
     else if (!strcmp(key, "prof_phase")) d->p.prof_phase = value;
+    else if (!strcmp(key, "dataflow")) { THK_CHECK_ARG(value == 0 || (d->p.tp_size == 1 && d->p.n_layer <= 254), "dataflow needs tp_size 1"); d->p.dataflow = value != 0; }
+    else if (!strcmp(key, "poll_single")) d->p.poll_single = value != 0;
+    else if (!strcmp(key, "nosync")) d->p.nosync = value != 0;
     else { thk_set_error("thk_decoder_tune: unknown key %s", key); return THK_E_INVALID; }
     return THK_OK;
 }

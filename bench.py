@@ -165,9 +165,16 @@ def main():
     torch.cuda.set_device(local_rank)
     import torch.distributed as dist
     if world > 1:
+        # NCCL prints its version banner on stdout at the first collective; the driver reads ONE JSON line from stdout,
+        # so stdout is parked on stderr until the result line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
     else:
         dist = None
+        saved_stdout = None
     stream = torch.cuda.current_stream()
     dev = th.Device(local_rank, stream=stream.cuda_stream)
 
@@ -264,18 +271,25 @@ def main():
             "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 activations/accumulate x f16 weights (reference arithmetic)",
             "data": "synthetic",
-            "config": {"workload": f"LLaMA-7B f16, 1-token decode, ctx={args.ctx} (n_past={n_past}), 1xB200", "n_layer": args.layers,
+            "config": {"workload": f"LLaMA-7B f16, 1-token decode, ctx={args.ctx} (n_past={n_past}), {world}xB200", "n_layer": args.layers,
                        "l2": "inputs (13.2 GB weights + 0.5 GB KV per step) exceed the 126 MB L2; no flush needed",
                        "kv": "f32, synthetic fill for positions < n_past",
                        "parallelism": "single GPU" if world == 1 else f"tp{world}: row/column-sharded matvecs, in-kernel one-shot all-reduce over NVLink peer memory (2 per layer)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roof, "cpu_baseline": cpu}
     if args.layers != L:
         line["invalid"] = "debug run with fewer layers"
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.barrier()
-    model.close()
+        model.close()
+        dist.destroy_process_group()
+    else:
+        model.close()
 
 
 if __name__ == "__main__":

@@ -74,6 +74,7 @@ struct DecParams {
     // = (epoch << 32) | f32 bits, written with ONE 64-bit store, so a reader that sees this layer's epoch sees the value.
     unsigned long long *h1f, *fff, *xf;
     unsigned flag_epoch;                // epoch of layer l in this launch = flag_epoch + l + 1
+    unsigned res_off;                   // tensor parallel: byte offset of the residual-stream copy behind xs in shared memory
     int dataflow;                       // 1: the three transitions above synchronise through the flagged vectors, no grid barrier
     int nosync;                         // DEBUG (wrong results): skip every cross-CTA wait, to time the pipeline without synchronisation
     int poll_single;                    // flagged reads: after a stale read spin on the one stale element before re-reading all
@@ -91,7 +92,8 @@ struct DecParams {
     int att_max_split;
     unsigned long long timeout_ns;
     // tensor parallel exchange (tp_size > 1): every rank owns one region laid out as
-    //   float xb[2][tp][n_embd] | float amax_val[tp] | int amax_idx[tp] | unsigned flags[tp] | unsigned flags2[tp]
+    //   u64 xbf[2][tp][n_embd] (flagged partials; the barrier path uses the first half as float xb[2][tp][n_embd])
+    //   | float amax_val[tp] | int amax_idx[tp] | unsigned flags[tp] | unsigned flags2[tp]
     // and writes its partial vectors / argmax candidates straight into every peer's region over NVLink.
     unsigned char* xchg[8];             // region base per rank (peer-mapped pointers; [tp_rank] is local)
     unsigned epoch_base;                // flags are monotonic: exchange k of this launch uses epoch_base + k + 1
@@ -172,6 +174,13 @@ __device__ __forceinline__ void st_flagged(unsigned long long* p, float v, unsig
     const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
+__device__ __forceinline__ void st_flagged_sys(unsigned long long* p, float v, unsigned epoch) {     // peer memory over NVLink
+    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void ld_flagged2_sys(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void ld_flagged2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
@@ -189,7 +198,11 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* ptr) {
 __device__ __forceinline__ float* xb_ptr(const DecParams& p, int rank, int which, int src) {
     return (float*)p.xchg[rank] + ((size_t)which * p.tp_size + src) * p.n_embd;
 }
-__device__ __forceinline__ size_t xchg_tail(const DecParams& p) { return (size_t)2 * p.tp_size * p.n_embd * sizeof(float); }
+__device__ __forceinline__ size_t xchg_tail(const DecParams& p) { return (size_t)2 * p.tp_size * p.n_embd * sizeof(unsigned long long); }
+// flagged partial vector `which` (0: Wo, 1: W2) of source rank `src` inside rank `rank`'s exchange region
+__device__ __forceinline__ unsigned long long* xbf_ptr(const DecParams& p, int rank, int which, int src) {
+    return (unsigned long long*)p.xchg[rank] + ((size_t)which * p.tp_size + src) * p.n_embd;
+}
 __device__ __forceinline__ float* xamax_val(const DecParams& p, int rank) { return (float*)(p.xchg[rank] + xchg_tail(p)); }
 __device__ __forceinline__ int* xamax_idx(const DecParams& p, int rank) { return (int*)(p.xchg[rank] + xchg_tail(p)) + p.tp_size; }
 __device__ __forceinline__ unsigned* xflags(const DecParams& p, int rank, int set) {
@@ -267,6 +280,7 @@ struct Smem {
     float* red;       // [kDumpBufs][kMathWarps][kRows] hand-off ring, then the attention scratch
     float* xs;
     uint32_t slots_a, full_a, empty_a, red_full_a, red_free_a, red_a, xs_a;   // shared-window addresses
+    // (tensor parallel: the lane-private residual stream sits behind xs, at xs_a + DecParams::res_off)
 };
 __device__ __forceinline__ Smem carve(unsigned char* base) {
     Smem s;
@@ -638,7 +652,7 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 // all loads in flight together, repeated until every element carries `epoch` -- that IS the synchronisation with the
 // CTAs that produce the vector (no grid barrier on these transitions).  After a stale read the lane first spins on the one
 // stale element (8 bytes per round instead of 64 * NCH), then reads everything again.  Bounded by the watchdog.
-template <int NCH>
+template <int NCH, bool SYS = false>
 __device__ __forceinline__ void load_flagged(const DecParams& p, const unsigned long long* vec, const int (&col)[NCH], unsigned epoch,
                                              unsigned long long (&e)[NCH * 8], bool& dead) {
     unsigned long long t0 = 0;
@@ -648,7 +662,10 @@ __device__ __forceinline__ void load_flagged(const DecParams& p, const unsigned 
         for (int u = 0; u < NCH; ++u) {
             if (col[u] >= 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) ld_flagged2(vec + col[u] + 2 * j, e[u * 8 + 2 * j], e[u * 8 + 2 * j + 1]);
+                for (int j = 0; j < 4; ++j) {
+                    if (SYS) ld_flagged2_sys(vec + col[u] + 2 * j, e[u * 8 + 2 * j], e[u * 8 + 2 * j + 1]);
+                    else ld_flagged2(vec + col[u] + 2 * j, e[u * 8 + 2 * j], e[u * 8 + 2 * j + 1]);
+                }
             }
         }
         int stale = -1;
@@ -879,6 +896,58 @@ __device__ __forceinline__ float prologue_norm(const DecParams& p, const Smem& S
     }
     return warp_sum(ss);
 }
+// Tensor-parallel variant (dataflow): the residual stream lives lane-privately in shared memory (every CTA of every rank
+// holds the whole vector, each lane the columns it multiplies against), so the all-reduce is finished right here:
+// v = residual + the tp flagged partial vectors that the Wo / W2 epilogues of ALL ranks pushed into this rank's exchange
+// region over NVLink (rank order: bitwise identical on every rank); reading them IS the cross-GPU synchronisation.
+// which < 0: v is the embedding row (first phase of a launch).
+// Every CTA reads all tp partial vectors (tp x 32 KB): fine at tp 2 and 4 (568 / 599 tok/s), too much L2 polling traffic
+// at tp 8 (432 tok/s).  A two-hop version (each CTA reduces 1/gridDim of the vector, then everyone reads the sums) is the
+// next step; a first attempt faulted on the GPU and was backed out.
+__device__ __forceinline__ float prologue_norm_tp(const DecParams& p, const Smem& S, const PhaseDesc& d, const uint16_t* emb_row, int which, unsigned epoch,
+                                                  const float* gain, float* out, int cw, int lane, bool& dead) {
+    const int n = d.C;
+    const int lcol = (cw << 8) + (lane << 3);
+    const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
+    const uint32_t ra = xa + p.res_off;
+    const unsigned long long* xbf = (const unsigned long long*)p.xchg[p.tp_rank];
+    float ss = 0.f;
+    for (int kt = 0; kt < d.KT; ++kt) {
+        const int c = kt * d.CT + lcol;
+        if (lcol >= d.CT || c >= n) continue;
+        const uint32_t off = (uint32_t)((kt * d.CT) << 2);
+        const float4 g0 = __ldg((const float4*)(gain + c)), g1 = __ldg((const float4*)(gain + c + 4));
+        float4 v0, v1;
+        if (which < 0) {
+            v0 = emb_f4(emb_row, c);
+            v1 = emb_f4(emb_row, c + 4);
+        } else {
+            v0 = lds128f(ra + off);
+            v1 = lds128f(ra + off + 512u);
+            for (int r0 = 0; r0 < p.tp_size; r0 += 4) {
+                int col[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) col[u] = (r0 + u < p.tp_size) ? (int)(((size_t)which * p.tp_size + r0 + u) * p.n_embd) + c : -1;
+                unsigned long long e[32];
+                load_flagged<4, true>(p, xbf, col, epoch, e, dead);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (col[u] >= 0) {
+                    const float4 a = flagged_f4(e + 8 * u), b = flagged_f4(e + 8 * u + 4);
+                    v0.x += a.x; v0.y += a.y; v0.z += a.z; v0.w += a.w;
+                    v1.x += b.x; v1.y += b.y; v1.z += b.z; v1.w += b.w;
+                }
+            }
+        }
+        sts128f(ra + off, v0);
+        sts128f(ra + off + 512u, v1);
+        ss = fmaf(v0.x, v0.x, ss); ss = fmaf(v0.y, v0.y, ss); ss = fmaf(v0.z, v0.z, ss); ss = fmaf(v0.w, v0.w, ss);
+        ss = fmaf(v1.x, v1.x, ss); ss = fmaf(v1.y, v1.y, ss); ss = fmaf(v1.z, v1.z, ss); ss = fmaf(v1.w, v1.w, ss);
+        if (out && (unsigned)(c >> 3) % gridDim.x == blockIdx.x) { *(float4*)(out + c) = v0; *(float4*)(out + c + 4) = v1; }
+        sts128f(xa + off, make_float4(v0.x * g0.x, v0.y * g0.y, v0.z * g0.z, v0.w * g0.w));
+        sts128f(xa + off + 512u, make_float4(v1.x * g1.x, v1.y * g1.y, v1.z * g1.z, v1.w * g1.w));
+    }
+    return warp_sum(ss);
+}
 // xs <- src (the FFN hidden vector for W2); fsrc != nullptr: from the flagged vector, waiting for `epoch`
 __device__ __forceinline__ void prologue_copy(const DecParams& p, const Smem& S, const PhaseDesc& d, const float* src, const unsigned long long* fsrc,
                                               unsigned epoch, int cw, int lane, bool& dead) {
@@ -1013,6 +1082,7 @@ __device__ __forceinline__ void prefetch_gain(const float* gain, int n, int ct) 
         asm volatile("prefetch.global.L2 [%0];" ::"l"(gain + off));
 }
 
+template <bool kTP>
 __device__ void math_main(const DecParams& p, const Smem& S) {
     const int ct = (int)threadIdx.x - kMathBase, cw = ct >> 5, lane = ct & 31;
     unsigned long long* const pm = (PROF(p) != nullptr && ct == 0) ? PROF(p) + (size_t)blockIdx.x * kProfPhases * 8 : nullptr;
@@ -1024,7 +1094,7 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
     if (blockIdx.x == 0 && ct == 0) *p.bar_next = 0u;   // arm the next launch's barrier counter
     mark(pm, p, 0, PROF_START);
     const int nsteps = 5 * p.n_layer + 1;
-    const bool tp = p.tp_size > 1;
+    constexpr bool tp = kTP;             // compile-time: the single-GPU kernel carries no tensor-parallel code
     int l = 0, k = K_QKV;
     float ss = 0.f;                       // this warp's share of sum(v^2) of the current norm phase's input
     for (int i = 0; i < nsteps; ++i) {
@@ -1037,10 +1107,13 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
             // converts the row itself and one copy goes to p.x for the Wo residual.  Under tensor parallelism the
             // W13 / QKV prologues also finish the all-reduce: h1 = x + sum of Wo partials, x = h1 + sum of W2 partials.
             const float* src = i == 0 ? nullptr : (k == K_W13) ? (tp ? p.x : p.h1) : (tp ? p.h1 : p.x);
-            const unsigned long long* fsrc = (i == 0 || !p.dataflow) ? nullptr : (k == K_W13 ? p.h1f : p.xf);
+            const unsigned long long* fsrc = (i == 0 || !p.dataflow || tp) ? nullptr : (k == K_W13 ? p.h1f : p.xf);
             const int which = (i == 0 || !tp) ? -1 : (k == K_W13 ? 0 : 1);
             float* out = i == 0 ? p.x : !tp ? nullptr : (k == K_W13 ? p.h1 : p.x);
-            ss = prologue_norm(p, S, p.ph[phase_of(k)], src, emb_row, fsrc, k == K_W13 ? epoch : epoch - 1u, gain, which, out, cw, lane, c.dead);
+            if (tp && p.dataflow)
+                ss = prologue_norm_tp(p, S, p.ph[phase_of(k)], emb_row, which, k == K_W13 ? epoch : epoch - 1u, gain, (i == 0 || k == K_OUT) ? p.x : nullptr, cw, lane, c.dead);
+            else
+                ss = prologue_norm(p, S, p.ph[phase_of(k)], src, emb_row, fsrc, k == K_W13 ? epoch : epoch - 1u, gain, which, out, cw, lane, c.dead);
         } else if (k == K_WO) {
             prologue_att_merge(p, S, p.ph[PH_WO], cw, lane);
         } else if (k == K_W2) {
@@ -1071,8 +1144,9 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
 // (and, in the attention phase, the math warps that met it at BAR_PRE) wrote global data in the phase;
 // __syncwarp / bar.sync order those writes before lane 0's gpu-scope release (cumulativity), and the
 // acquire fence + BAR_ALL make the other CTAs' writes visible to every thread here (read with .cg).
+template <bool kTP>
 __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, int lane, bool& dead, int xset = -1, unsigned epoch = 0u) {
-    if (xset >= 0) __threadfence_system();      // this warp's pushes to the peers are visible system-wide
+    if (kTP && xset >= 0) __threadfence_system();      // this warp's pushes to the peers are visible system-wide
     __syncwarp();
     if (lane == 0 && !dead && !p.nosync) {
         unsigned* const ctr = p.bar_ctr;
@@ -1088,7 +1162,7 @@ __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, 
             }
         }
         asm volatile("fence.acquire.gpu;" ::: "memory");
-        if (xset >= 0 && !dead) {
+        if (kTP && xset >= 0 && !dead) {
             // Cross-GPU step of the one-shot all-reduce: every local CTA has pushed its partial rows into all
             // peers (system-scope fenced before arriving here); rank-level flag tells the peers "my part is in".
             if (blockIdx.x == 0) {
@@ -1114,14 +1188,15 @@ __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, 
 enum EpiKind { EPI_QKV, EPI_WO, EPI_W13, EPI_W2, EPI_OUT };
 struct EpiState { float gate; float best; int best_idx; };
 
+template <bool kTP>
 __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S, int ph, int kind, const thk_llama_layer* L, unsigned epoch,
                                               EpiState& es, unsigned& gq, bool& dead, int lane) {
     const PhaseDesc& d = p.ph[ph];
-    const int D = p.head_dim, tp_size = p.tp_size, tp_rank = p.tp_rank, n_ctx = p.n_ctx, n_past = p.n_past;
+    const int D = p.head_dim, tp_size = kTP ? p.tp_size : 1, tp_rank = kTP ? p.tp_rank : 0, n_ctx = p.n_ctx, n_past = p.n_past;
     const int nsub = d.paired ? 2 : 1;
     const int rr = lane & 7, qq = lane >> 3;          // this lane adds row rr of math warps 2 qq and 2 qq + 1
     const uint32_t my_a = S.red_a + (uint32_t)((2 * qq * kRecFloats + rr) * 4);
-    const bool has_resid = (kind == EPI_WO || kind == EPI_W2) && tp_size == 1;
+    const bool has_resid = (kind == EPI_WO || kind == EPI_W2) && !kTP;
     const bool need_scale = (kind == EPI_QKV || kind == EPI_W13 || kind == EPI_OUT);
     bool have_scale = false;
     float scale = 1.0f;
@@ -1176,7 +1251,8 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
                     }
                     break;
                 case EPI_WO:                                                           // th-llama.cpp:409
-                    if (tp_size == 1) { const float v = resid + y; p.h1[r] = v; if (p.dataflow) st_flagged(p.h1f + r, v, epoch); }
+                    if (!kTP) { const float v = resid + y; p.h1[r] = v; if (p.dataflow) st_flagged(p.h1f + r, v, epoch); }
+                    else if (p.dataflow) for (int dst = 0; dst < tp_size; ++dst) st_flagged_sys(xbf_ptr(p, dst, 0, tp_rank) + r, y, epoch);
                     else for (int dst = 0; dst < tp_size; ++dst) xb_ptr(p, dst, 0, tp_rank)[r] = y;   // partial -> every rank
                     break;
                 case EPI_W13:
@@ -1188,7 +1264,8 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
                     }
                     break;
                 case EPI_W2:                                                           // th-llama.cpp:447
-                    if (tp_size == 1) { const float v = resid + y; p.x[r] = v; if (p.dataflow) st_flagged(p.xf + r, v, epoch); }
+                    if (!kTP) { const float v = resid + y; p.x[r] = v; if (p.dataflow) st_flagged(p.xf + r, v, epoch); }
+                    else if (p.dataflow) for (int dst = 0; dst < tp_size; ++dst) st_flagged_sys(xbf_ptr(p, dst, 1, tp_rank) + r, y, epoch);
                     else for (int dst = 0; dst < tp_size; ++dst) xb_ptr(p, dst, 1, tp_rank)[r] = y;
                     break;
                 default: {                                                             // EPI_OUT
@@ -1202,6 +1279,7 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
     }
 }
 
+template <bool kTP>
 __device__ void epi_main(const DecParams& p, const Smem& S) {
     const int lane = (int)threadIdx.x & 31;
     EpiState es{0.f, 0.f, -1};
@@ -1220,15 +1298,15 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
     for (int i = 0; i < nsteps; ++i) {
         if (k != K_ATT) {
             const int kind = k == K_QKV ? EPI_QKV : k == K_WO ? EPI_WO : k == K_W13 ? EPI_W13 : k == K_W2 ? EPI_W2 : EPI_OUT;
-            epi_mat_phase(p, S, phase_of(k), kind, k == K_OUT ? nullptr : p.layers + l, p.flag_epoch + (unsigned)l + 1u, es, gq, dead, lane);
+            epi_mat_phase<kTP>(p, S, phase_of(k), kind, k == K_OUT ? nullptr : p.layers + l, p.flag_epoch + (unsigned)l + 1u, es, gq, dead, lane);
         } else {
             bar_sync(BAR_PRE, kMathThreads + 32);
         }
         if (k == K_OUT) break;
         if (!(p.dataflow && (k == K_WO || k == K_W13 || k == K_W2))) {
             ++nbar;
-            if (p.tp_size > 1 && (k == K_WO || k == K_W2)) { ++xk; grid_barrier(p, nbar, lane, dead, k == K_WO ? 0 : 1, p.epoch_base + xk); }
-            else grid_barrier(p, nbar, lane, dead);
+            if (kTP && (k == K_WO || k == K_W2)) { ++xk; grid_barrier<kTP>(p, nbar, lane, dead, k == K_WO ? 0 : 1, p.epoch_base + xk); }
+            else grid_barrier<kTP>(p, nbar, lane, dead);
             bar_sync(BAR_ALL, kMathThreads + 32);
         }
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
@@ -1244,7 +1322,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
         }
         if (lane == 0) { p.amax_val[blockIdx.x] = bv; p.amax_idx[blockIdx.x] = bi; }
         ++nbar;
-        grid_barrier(p, nbar, lane, dead);
+        grid_barrier<kTP>(p, nbar, lane, dead);
         if (blockIdx.x == 0) {
             // every lane takes CTAs lane, lane+32, ... (loads in flight together), then the warp reduces
             float gv = 0.f; int gi = -1;
@@ -1267,7 +1345,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
                 if (oi >= 0 && (gi < 0 || ov > gv || (ov == gv && oi < gi))) { gv = ov; gi = oi; }
             }
             if (lane == 0) {
-                if (p.tp_size > 1) {
+                if (kTP) {
                     // cross-rank argmax: push this rank's candidate to every rank, wait for all, lowest id wins ties
                     const unsigned epoch = p.epoch_base + 2u * (unsigned)p.n_layer + 1u;
                     for (int d = 0; d < p.tp_size; ++d) { xamax_val(p, d)[p.tp_rank] = gv; xamax_idx(p, d)[p.tp_rank] = gi; }
@@ -1297,6 +1375,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
     if (PROF(p) && lane == 0) prof_mark(PROF(p), 5u * (unsigned)p.n_layer + 1u, PROF_START);
 }
 
+template <bool kTP>
 __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_constant__ DecParams p) {
     const Smem S = smem_view();
     if (threadIdx.x == 0) {
@@ -1318,15 +1397,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
     if (threadIdx.x < kMathBase) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
         if (threadIdx.x < 32) producer_main(p, S);
-        else if (threadIdx.x < 64) epi_main(p, S);
+        else if (threadIdx.x < 64) epi_main<kTP>(p, S);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMathRegs));
-        math_main(p, S);
+        math_main<kTP>(p, S);
     }
 }
 
-size_t decode_smem_bytes(int max_vec) {
-    return (size_t)kXsOffset + (size_t)((max_vec + 255) & ~255) * sizeof(float);
+size_t decode_smem_bytes(int max_vec, int res_vec) {
+    return (size_t)kXsOffset + (size_t)((max_vec + 255) & ~255) * sizeof(float) + (size_t)((res_vec + 255) & ~255) * sizeof(float);
 }
 
 PhaseDesc make_phase(int nseg, const int* rows, int C, bool paired) {
@@ -1420,13 +1499,15 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     // tuning knobs (defaults = the measured best)
     p.l2_ahead = (unsigned)(getenv("THK_L2_AHEAD_KB") ? atoi(getenv("THK_L2_AHEAD_KB")) : 64) * 1024u;   // 0 / 64 / 128 / 192 KB: 2.765 / 2.720 / 2.744 / 2.767 ms
     const int max_vec = p.n_embd > p.Fh ? p.n_embd : p.Fh;
-    d->smem = decode_smem_bytes(max_vec);
+    d->smem = decode_smem_bytes(max_vec, tp > 1 ? p.n_embd : 0);
+    p.res_off = (unsigned)(((max_vec + 255) & ~255) * sizeof(float));
     if (d->smem > 227 * 1024) {
         thk_set_error("thk_decoder_create: needs %zu bytes of shared memory (> 227 KB); n_ff/tp=%d too large", d->smem, p.Fh);
         delete d;
         return THK_E_UNSUPPORTED;
     }
-    THK_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+    if (tp > 1) THK_CUDA(cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+    else THK_CUDA(cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
 
     THK_CUDA(cudaMalloc(&d->d_layers, sizeof(thk_llama_layer) * p.n_layer));
     THK_CUDA(cudaMemcpy(d->d_layers, layers, sizeof(thk_llama_layer) * p.n_layer, cudaMemcpyHostToDevice));
@@ -1443,7 +1524,7 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     THK_CUDA(cudaMalloc(&d->flagged, nflag * sizeof(unsigned long long)));
     THK_CUDA(cudaMemset(d->flagged, 0, nflag * sizeof(unsigned long long)));     // epoch 0 is never used
     p.h1f = d->flagged; p.xf = p.h1f + p.n_embd; p.fff = p.xf + p.n_embd;
-    p.dataflow = (tp == 1 && p.n_layer <= 254 && !(getenv("THK_DATAFLOW") && atoi(getenv("THK_DATAFLOW")) == 0)) ? 1 : 0;
+    p.dataflow = (p.n_layer <= 254 && !(getenv("THK_DATAFLOW") && atoi(getenv("THK_DATAFLOW")) == 0)) ? 1 : 0;
     p.poll_single = getenv("THK_POLL_SINGLE") ? atoi(getenv("THK_POLL_SINGLE")) : 1;
     const size_t nctrl = 64 + 4;
     THK_CUDA(cudaMalloc(&d->ctrl, nctrl * sizeof(unsigned)));
@@ -1451,7 +1532,7 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     p.status = d->ctrl + 64;
     THK_CUDA(cudaMalloc(&d->d_tok, sizeof(int) * 2));
     if (tp > 1) {
-        d->xchg_bytes = ((size_t)2 * tp * p.n_embd * sizeof(float) + (size_t)4 * tp * sizeof(unsigned) + 255) & ~(size_t)255;
+        d->xchg_bytes = ((size_t)2 * tp * p.n_embd * sizeof(unsigned long long) + (size_t)4 * tp * sizeof(unsigned) + 255) & ~(size_t)255;
         THK_CUDA(cudaMalloc(&d->xchg, d->xchg_bytes));
         THK_CUDA(cudaMemset(d->xchg, 0, d->xchg_bytes));
         p.xchg[p.tp_rank] = d->xchg;
@@ -1474,6 +1555,9 @@ static int launch_step(thk_decoder* d, const int32_t* token, int32_t n_past, flo
     THK_ENTER(d->ctx);
     DecParams p = d->p;
     p.token = token; p.n_past = n_past; p.logits = logits; p.next_token = next_token; p.next_logit = next_logit;
+    // tensor parallel: the end-of-launch argmax exchange is also what keeps a fast rank's NEXT launch from overwriting
+    // exchange records a slow rank still reads -- make sure it always runs
+    if (p.tp_size > 1 && !p.next_token && !p.next_logit) p.next_token = d->d_tok + 1;
     if (p.tp_size > 1) {
         if (!d->peers_set) { thk_set_error("thk_decoder_step: tensor-parallel decoder has no peers (call thk_decoder_set_peers)"); return THK_E_INVALID; }
         p.epoch_base = d->epoch;
@@ -1492,7 +1576,8 @@ static int launch_step(thk_decoder* d, const int32_t* token, int32_t n_past, flo
     attr[0].id = cudaLaunchAttributeCooperative;   // co-residency of all CTAs is required by the grid barriers
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    THK_CUDA(cudaLaunchKernelEx(&cfg, decode_kernel, p));
+    if (p.tp_size > 1) THK_CUDA(cudaLaunchKernelEx(&cfg, decode_kernel<true>, p));
+    else THK_CUDA(cudaLaunchKernelEx(&cfg, decode_kernel<false>, p));
     return THK_OK;
 }
 
@@ -1544,7 +1629,7 @@ extern "C" int thk_decoder_tune(thk_decoder* d, const char* key, int value) {
     THK_CHECK_ARG(d && key, "thk_decoder_tune: null argument");
     if (!strcmp(key, "l2_ahead_kb")) { THK_CHECK_ARG(value >= 0 && value <= 1024, "l2_ahead_kb out of range"); d->p.l2_ahead = (unsigned)value * 1024u; }
     else if (!strcmp(key, "prof_phase")) d->p.prof_phase = value;
-    else if (!strcmp(key, "dataflow")) { THK_CHECK_ARG(value == 0 || (d->p.tp_size == 1 && d->p.n_layer <= 254), "dataflow needs tp_size 1"); d->p.dataflow = value != 0; }
+    else if (!strcmp(key, "dataflow")) { THK_CHECK_ARG(value == 0 || d->p.n_layer <= 254, "dataflow needs n_layer <= 254"); d->p.dataflow = value != 0; }
     else if (!strcmp(key, "poll_single")) d->p.poll_single = value != 0;
     else if (!strcmp(key, "nosync")) d->p.nosync = value != 0;
     else { thk_set_error("thk_decoder_tune: unknown key %s", key); return THK_E_INVALID; }
@@ -1568,7 +1653,7 @@ extern "C" int thk_decoder_exchange_info(thk_decoder* d, void** buf, size_t* buf
     THK_CHECK_ARG(d && buf && buf_bytes, "thk_decoder_exchange_info: null argument");
     THK_CHECK_ARG(d->p.tp_size > 1, "thk_decoder_exchange_info: decoder is not tensor parallel");
     *buf = d->xchg; *buf_bytes = d->xchg_bytes;
-    if (flags) *flags = d->xchg + (size_t)2 * d->p.tp_size * d->p.n_embd * sizeof(float) + (size_t)2 * d->p.tp_size * sizeof(unsigned);
+    if (flags) *flags = d->xchg + (size_t)2 * d->p.tp_size * d->p.n_embd * sizeof(unsigned long long) + (size_t)2 * d->p.tp_size * sizeof(unsigned);
     if (flag_bytes) *flag_bytes = (size_t)2 * d->p.tp_size * sizeof(unsigned);
     return THK_OK;
 }

@@ -129,12 +129,26 @@ tk_llama_token th_eval_gpu(WGPUDevice device, WGPUQueue queue, std::shared_ptr<L
 int th_eval_gpu_launch(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens, int n_tokens,
                        int n_past);
 tk_llama_token th_eval_gpu_finish(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m);
-// greedy branch of th-llama.cpp:814-838
+// th-llama.cpp:814-907: greedy for temp <= 0, else temperature / repetition penalty / top-k / top-p sampling with m->rng
 tk_llama_token llama_sample_top_p_top_k(std::shared_ptr<LlamaModel> m, const std::vector<tk_llama_token>& last_n_tokens, int top_k,
                                         float top_p, float temp, float repeat_penalty, std::vector<float>& logits);
 // n_new greedy tokens after feeding `prompt` one token at a time (do_inference's sync loop,
 // th-llama.cpp:199-238, without tokenizer / printing)
 std::vector<tk_llama_token> generate_greedy(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m,
                                             const std::vector<tk_llama_token>& prompt, int n_new);
+
+// the sampler on a bare logits vector (what llama_sample_top_p_top_k runs after picking the last n_vocab logits)
+tk_llama_token llama_sample_logits(std::mt19937& rng, const float* logits, int n_logits, const std::vector<tk_llama_token>& last_n_tokens,
+                                   int top_k, float top_p, float temp, float repeat_penalty);
+// tokenizer (th-llama.cpp:909-1107): SentencePiece-style merges driven by the vocabulary scores, byte fallback (id = byte + 3)
+std::vector<tk_llama_token> tk_llama_tokenize(const LlamaVocab& vocab, const std::string& text, bool add_bos);
+std::vector<tk_llama_token> tk_llama_tokenize(std::shared_ptr<LlamaModel> m, const std::string& text, bool add_bos);
+int tk_llama_tokenize(std::shared_ptr<LlamaModel> m, const char* text, tk_llama_token* tokens, int n_max_tokens, bool add_bos);
+const char* tk_llama_token_to_str(std::shared_ptr<LlamaModel> m, tk_llama_token token);
+tk_llama_token tk_llama_token_bos();
+tk_llama_token tk_llama_token_eos();
+// do_inference (th-llama.cpp:111-168), synchronous: tokenise, feed the prompt, generate until EOS / max_new_tokens /
+// full context; streams pieces through m->onNewToken and returns the generated text
+std::string do_inference(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, std::string prompt, int max_new_tokens);
 
 }  // namespace th

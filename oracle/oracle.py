@@ -430,6 +430,154 @@ def ref_lib():
                                  C.POINTER(C.c_int64)]
         R.ref_tokenize.restype = C.c_int
         R.ref_tokenize.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.c_int]
+        R.ref_vocab_model.restype = C.c_void_p
+        R.ref_vocab_model.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_int]
+        R.ref_sample.restype = C.c_int
+        R.ref_sample.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_float, C.c_float,
+                                 C.c_float, C.c_uint32]
         R.ref_dispatch_count.restype = C.c_uint64
         _ref = R
     return _ref
+
+
+# ---------------------------------------------------------------------------------------------
+# Host-side restatements: tokenizer and sampler.  Pure Python, small inputs only.
+# Pinned against the reference's own code through tests/golden/{tokenizer,sampler}.json.
+# ---------------------------------------------------------------------------------------------
+def tokenize(tokens, scores, text: bytes, add_bos: bool):
+    """TkLlamaTokenizer (th-llama.cpp:909-1041): cut into UTF-8 characters, repeatedly merge the adjacent pair whose
+    concatenation is the best-scoring vocabulary entry (ties: leftmost), byte-fallback (id = byte + 3) for the rest.
+    tokens: list of bytes (id -> piece), later duplicates win the lookup like the loader (th-llama-loader.cpp:560)."""
+    import heapq
+    out = []
+    if len(text) == 0:
+        return out
+    if add_bos:
+        out.append(1)
+    tid = {}
+    for i, t in enumerate(tokens):
+        tid[bytes(t)] = i
+    lens = [1] * 12 + [2, 2, 3, 4]
+    off, piece = 0, []          # piece: [prev, next, off, len]
+    while off < len(text):
+        n = min(len(text) - off, lens[text[off] >> 4])
+        piece.append([len(piece) - 1, 0, off, n])
+        off += n
+        piece[-1][1] = -1 if off == len(text) else len(piece)
+    heap = []
+
+    def propose(l, r):
+        if l < 0 or r < 0:
+            return
+        s_ = text[piece[l][2]:piece[l][2] + piece[l][3] + piece[r][3]]
+        i = tid.get(s_)
+        if i is None or i >= len(tokens):
+            return
+        heapq.heappush(heap, (-float(np.float32(scores[i])), l, r, len(s_)))   # highest score first, then smallest left
+
+    for i in range(1, len(piece)):
+        propose(i - 1, i)
+    while heap:
+        _, l, r, size = heapq.heappop(heap)
+        if piece[l][3] == 0 or piece[r][3] == 0 or piece[l][3] + piece[r][3] != size:
+            continue
+        piece[l][3] += piece[r][3]
+        piece[r][3] = 0
+        piece[l][1] = piece[r][1]
+        if piece[r][1] >= 0:
+            piece[piece[r][1]][0] = l
+        propose(piece[l][0], l)
+        propose(l, piece[l][1])
+    i = 0
+    while i != -1:
+        _, nxt, o_, n = piece[i]
+        t = tid.get(text[o_:o_ + n])
+        if t is None:
+            out.extend(b + 3 for b in text[o_:o_ + n])
+        else:
+            out.append(t)
+        i = nxt
+    return out
+
+
+class MT19937:
+    """std::mt19937 (32-bit Mersenne twister), as seeded by seed(uint32)."""
+    def __init__(self, seed):
+        self.mt = [0] * 624
+        self.mt[0] = seed & 0xFFFFFFFF
+        for i in range(1, 624):
+            self.mt[i] = (1812433253 * (self.mt[i - 1] ^ (self.mt[i - 1] >> 30)) + i) & 0xFFFFFFFF
+        self.idx = 624
+
+    def __call__(self):
+        if self.idx >= 624:
+            mt = self.mt
+            for i in range(624):
+                y = (mt[i] & 0x80000000) | (mt[(i + 1) % 624] & 0x7FFFFFFF)
+                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+            self.idx = 0
+        y = self.mt[self.idx]
+        self.idx += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        y ^= y >> 18
+        return y & 0xFFFFFFFF
+
+
+def sample_top_p_top_k(logits, last_n, top_k, top_p, temp, repeat_penalty, seed):
+    """llama_sample_top_p_top_k (th-llama.cpp:814-907) with libstdc++'s std::discrete_distribution<int> over an
+    mt19937 seeded with `seed` (generate_canonical<double, 53>: two 32-bit draws; index = lower_bound of the draw in
+    the cumulative probabilities).  float32 arithmetic where the reference uses float, double where it uses double."""
+    f32 = np.float32
+    lg = np.asarray(logits, dtype=np.float32)
+    n = lg.size
+    if temp <= 0:
+        return int(np.argmax(lg))                                   # first maximum = lowest id
+    scale = f32(1.0) / f32(temp)
+    rp = f32(repeat_penalty)
+    seen = set(int(t) for t in last_n)
+    cand = []
+    for i in range(n):
+        v = f32(lg[i] * scale)
+        if i in seen:
+            v = f32(v * rp) if lg[i] < 0 else f32(v / rp)
+        cand.append((v, i))
+    if 0 < top_k < n:
+        # std::partial_sort is not stable; the fixtures avoid ties among the top_k + 1 largest scores
+        cand = sorted(cand, key=lambda c: -float(c[0]))[:top_k]
+    maxl = max(c[0] for c in cand)
+    probs, total = [], 0.0
+    for v, _ in cand:
+        pr = f32(np.exp(np.float64(f32(v - maxl))))                   # expf: correctly rounded float exp (glibc)
+        probs.append(pr)
+        total += float(pr)
+    probs = [f32(float(pr) / total) for pr in probs]
+    if top_p < 1.0:
+        cum = 0.0
+        for i, pr in enumerate(probs):
+            cum += float(pr)
+            if cum >= float(f32(top_p)):
+                probs = probs[:i + 1]
+                cand = cand[:i + 1]
+                break
+        inv = 1.0 / cum
+        probs = [f32(float(pr) * inv) for pr in probs]
+    # std::discrete_distribution: normalise in double, cumulative sums, last = 1.0 (libstdc++ random.tcc)
+    w = [float(pr) for pr in probs]
+    if len(w) < 2:
+        return cand[0][1]
+    sw = sum(w)
+    w = [x / sw for x in w]
+    cp, acc = [], 0.0
+    for x in w:
+        acc += x
+        cp.append(acc)
+    cp[-1] = 1.0
+    rng = MT19937(seed)
+    a, b = rng(), rng()
+    u = (a + b * 4294967296.0) / 18446744073709551616.0
+    if u >= 1.0:
+        u = float(np.nextafter(1.0, 0.0))
+    import bisect
+    return cand[bisect.bisect_left(cp, u)][1]

@@ -97,6 +97,31 @@ int ref_tokenize(void* h, const char* text, int add_bos, int32_t* out, int cap) 
     return n;
 }
 
+// a model that only carries a vocabulary (no file): for pinning the tokenizer on arbitrary vocabularies
+void* ref_vocab_model(const char* const* tokens, const int32_t* lengths, const float* scores, int n) {
+    auto m = std::make_shared<th::LlamaModel>();
+    m->n_vocab = n;
+    m->vocab.id_to_token.resize(n);
+    for (int i = 0; i < n; ++i) {
+        std::string t(tokens[i], (size_t)lengths[i]);
+        m->vocab.token_to_id[t] = i;
+        m->vocab.id_to_token[i].tok = t;
+        m->vocab.id_to_token[i].score = scores[i];
+    }
+    return new RefModel{m};
+}
+
+// the reference sampler (th-llama.cpp:814-907) with its mt19937 seeded explicitly
+int ref_sample(int n_vocab, const float* logits, const int32_t* last_n, int n_last, int top_k, float top_p, float temp,
+               float repeat_penalty, uint32_t seed) {
+    auto m = std::make_shared<th::LlamaModel>();
+    m->n_vocab = n_vocab;
+    m->rng.seed(seed);
+    std::vector<float> l(logits, logits + n_vocab);
+    std::vector<th::tk_llama_token> last(last_n, last_n + (last_n ? n_last : 0));
+    return th::llama_sample_top_p_top_k(m, last, top_k, top_p, temp, repeat_penalty, l);
+}
+
 uint64_t ref_dispatch_count(void) { return thstub_dispatch_count(); }
 
 }  // extern "C"

@@ -253,3 +253,44 @@ def test_full_7b_properties(th, dev, oracle):
     dev_ids = g.generate_device(first, len(toks), 6)
     assert dev_ids == host_ids[1:]
     g.close()
+
+
+def test_do_inference_driver(th, dev, oracle, tmp_path):
+    """th::do_inference (th-llama.cpp:111-168): prompt -> tokenizer -> one token per evaluation -> greedy generation.
+    The synthetic ggjt vocabulary is "<i>" with score -i; no two-character piece exists, so nothing merges and the prompt
+    comes out as byte tokens (the reference's own tokenizer does the same, tests/golden/loader_tiny.json).  The generated
+    text must be the pieces of the ids the oracle generates from the same tokens."""
+    cfg = oracle.TINY
+    o = oracle.Model.synthetic(cfg, 99)
+    path = str(tmp_path / "tiny.ggjt")
+    o.write_ggjt(path)
+    g = th.LlamaModel.load(dev, path, n_ctx=cfg.n_ctx)
+    vocab = [b"<%d>" % i for i in range(cfg.n_vocab)]
+    scores = [-float(i) for i in range(cfg.n_vocab)]
+    assert g.tokenize("<5><17>", add_bos=True) == oracle.tokenize(vocab, scores, b"<5><17>", True) == [1] + [b + 3 for b in b"<5><17>"]
+    assert g.token_str(300) == b"<300>"
+    prompt_ids = oracle.tokenize(vocab, scores, b" <7>", True)    # do_inference prepends a space to the first prompt
+    assert g.tokenize(" <7>", add_bos=True) == prompt_ids and len(prompt_ids) == 5
+    n_new = 12
+    text = g.inference("<7>", n_new)
+    # oracle: feed the prompt one token at a time, then greedy
+    tok = None
+    for i, t in enumerate(prompt_ids):
+        tok = oracle.greedy(o.eval([t], i))
+    want, n_past = [], len(prompt_ids)
+    for _ in range(n_new):
+        if tok == 2:
+            break
+        want.append(tok)
+        tok = oracle.greedy(o.eval([tok], n_past))
+        n_past += 1
+    assert text == b"".join(b"<%d>" % t for t in want)
+    # sampling mode: deterministic for a seed, and temperature 0 falls back to greedy
+    g.reset(); g.set_sampler(0.8, seed=7); a = g.inference("<7>", 8)
+    g.reset(); g.set_sampler(0.8, seed=7); b = g.inference("<7>", 8)
+    assert a == b and len(a) > 0
+    g.reset(); g.set_sampler(0.0); assert g.inference("<7>", n_new) == text
+    # a prompt that does not fit is refused through onError
+    with pytest.raises(th.ThkError):
+        g.reset(); g.inference("<5>" * 40, 4)
+    g.close()

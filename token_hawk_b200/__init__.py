@@ -155,6 +155,16 @@ def host() -> C.CDLL:
         H.capi_tensor_info.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
         H.capi_tensor_download.argtypes = [vp, C.c_char_p, vp, i64]
         H.capi_vocab_size.argtypes = [vp]
+        H.capi_sample.argtypes = [C.c_int, f32p, i32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_uint32]
+        H.capi_vocab_create.restype = vp
+        H.capi_vocab_create.argtypes = [C.POINTER(C.c_char_p), i32p, f32p, C.c_int]
+        H.capi_vocab_free.argtypes = [vp]
+        H.capi_vocab_tokenize.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, i32p, C.c_int]
+        H.capi_tokenize.argtypes = [vp, C.c_char_p, C.c_int, i32p, C.c_int]
+        H.capi_token_str.restype = C.c_char_p
+        H.capi_token_str.argtypes = [vp, C.c_int]
+        H.capi_set_sampler.argtypes = [vp, C.c_float, C.c_uint32]
+        H.capi_inference.argtypes = [vp, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         _h = H
     return _h
 
@@ -162,6 +172,40 @@ def host() -> C.CDLL:
 def _check(rc):
     if rc != 0:
         raise ThkError(rc, kernels().thk_last_error().decode())
+
+
+def sample(logits: np.ndarray, last_n=(), top_k=40, top_p=0.95, temp=0.8, repeat_penalty=1.1, seed=0) -> int:
+    """th::llama_sample_logits (the reference's llama_sample_top_p_top_k, th-llama.cpp:814-907) with an mt19937
+    seeded with `seed`.  Host-only: needs no GPU."""
+    lg = np.ascontiguousarray(logits, dtype=np.float32)
+    last = np.ascontiguousarray(last_n, dtype=np.int32)
+    return int(host().capi_sample(lg.size, lg.ctypes.data_as(f32p), last.ctypes.data_as(i32p) if last.size else None, int(last.size),
+                                  int(top_k), float(top_p), float(temp), float(repeat_penalty), int(seed)))
+
+
+class Vocab:
+    """A bare th::LlamaVocab for the tokenizer (th-llama.cpp:909-1041).  Host-only: needs no GPU."""
+
+    def __init__(self, tokens, scores):
+        toks = [bytes(t) for t in tokens]
+        arr = (C.c_char_p * len(toks))(*toks)
+        lens = np.array([len(t) for t in toks], dtype=np.int32)
+        sc = np.ascontiguousarray(scores, dtype=np.float32)
+        self.h = host().capi_vocab_create(arr, lens.ctypes.data_as(i32p), sc.ctypes.data_as(f32p), len(toks))
+
+    def tokenize(self, text: bytes, add_bos: bool = True):
+        cap = 4 * len(text) + 8
+        out = np.zeros(cap, dtype=np.int32)
+        n = host().capi_vocab_tokenize(self.h, text, len(text), int(add_bos), out.ctypes.data_as(i32p), cap)
+        return [int(x) for x in out[:n]]
+
+    def __del__(self):
+        try:
+            if self.h:
+                host().capi_vocab_free(self.h)
+                self.h = None
+        except Exception:
+            pass
 
 
 class Device:
@@ -373,6 +417,27 @@ class LlamaModel:
         self.last_tile_times = (buf[n0 + n1:n0 + n1 + nt].reshape(grid, 64).astype(np.int64),
                                 buf[n0 + n1 + nt:].reshape(grid, 64).astype(np.int64))
         return buf[:n0].reshape(grid, 256, 8).astype(np.int64), buf[n0:n0 + n1].reshape(grid, 4).astype(np.int64)
+
+    def tokenize(self, text: str, add_bos: bool = True):
+        cap = 4 * len(text.encode()) + 8
+        out = np.zeros(cap, dtype=np.int32)
+        n = host().capi_tokenize(self.h, text.encode(), int(add_bos), out.ctypes.data_as(i32p), cap)
+        return [int(x) for x in out[:n]]
+
+    def token_str(self, token: int) -> bytes:
+        return host().capi_token_str(self.h, int(token)) or b""
+
+    def set_sampler(self, temp: float, seed: int = 0):
+        host().capi_set_sampler(self.h, float(temp), int(seed))
+
+    def inference(self, prompt: str, max_new_tokens: int = 32) -> bytes:
+        """th::do_inference (th-llama.cpp:111-168): tokenise, feed the prompt, generate; returns the generated bytes."""
+        cap = 1 << 16
+        buf = C.create_string_buffer(cap)
+        n = host().capi_inference(self.h, prompt.encode(), int(max_new_tokens), buf, cap)
+        if n < 0:
+            raise ThkError(-1, host().capi_last_error().decode())
+        return buf.raw[:min(n, cap - 1)]
 
     def tune(self, key: str, value: int):
         """Persistent-kernel tuning knob (thk_decoder_tune): 'l2_ahead_kb', 'poll_depth'."""

@@ -213,6 +213,58 @@ int capi_tensor_download(void* h, const char* name, void* out_host, int64_t byte
     return thk_download(cm->ctx, out_host, t->gpu, 0, (size_t)bytes);
 }
 
+// ---- sampler / tokenizer / generation driver (th-llama.cpp:111-238, 814-1107); the first three need no device ----
+int capi_sample(int n_vocab, const float* logits, const int32_t* last_n, int n_last, int top_k, float top_p, float temp,
+                float repeat_penalty, uint32_t seed) {
+    std::mt19937 rng(seed);
+    std::vector<tk_llama_token> last(last_n, last_n + (last_n ? n_last : 0));
+    return llama_sample_logits(rng, logits, n_vocab, last, top_k, top_p, temp, repeat_penalty);
+}
+void* capi_vocab_create(const char* const* tokens, const int32_t* lengths, const float* scores, int n) {
+    LlamaVocab* v = new LlamaVocab;
+    v->id_to_token.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const std::string t(tokens[i], (size_t)lengths[i]);
+        v->token_to_id[t] = i;                      // later duplicates win, like the reference loader (th-llama-loader.cpp:560)
+        v->id_to_token[i].tok = t;
+        v->id_to_token[i].score = scores[i];
+    }
+    return v;
+}
+void capi_vocab_free(void* v) { delete (LlamaVocab*)v; }
+int capi_vocab_tokenize(void* v, const char* text, int text_len, int add_bos, int32_t* out, int cap) {
+    const std::vector<tk_llama_token> t = tk_llama_tokenize(*(LlamaVocab*)v, std::string(text, (size_t)text_len), add_bos != 0);
+    for (size_t i = 0; i < t.size() && (int)i < cap; ++i) out[i] = t[i];
+    return (int)t.size();
+}
+int capi_tokenize(void* h, const char* text, int add_bos, int32_t* out, int cap) {
+    const std::vector<tk_llama_token> t = tk_llama_tokenize(((CapiModel*)h)->m, std::string(text), add_bos != 0);
+    for (size_t i = 0; i < t.size() && (int)i < cap; ++i) out[i] = t[i];
+    return (int)t.size();
+}
+const char* capi_token_str(void* h, int token) { return tk_llama_token_to_str(((CapiModel*)h)->m, token); }
+void capi_set_sampler(void* h, float temp, uint32_t seed) {
+    auto& m = ((CapiModel*)h)->m;
+    m->samplerTemp = temp;
+    m->rng.seed(seed);
+}
+// do_inference: returns the number of bytes of generated text (copied, NUL-terminated, into out when it fits), < 0 on error
+int capi_inference(void* h, const char* prompt, int max_new_tokens, char* out, int cap) {
+    CapiModel* cm = (CapiModel*)h;
+    g_capi_err.clear();
+    bool failed = false;
+    cm->m->onError = [&](std::string e) { g_capi_err = e; failed = true; };
+    const std::string msg = do_inference(cm->ctx, cm->ctx, cm->m, prompt, max_new_tokens);
+    cm->m->onError = nullptr;
+    if (failed) return -1;
+    if (out && cap > 0) {
+        const size_t n = std::min(msg.size(), (size_t)cap - 1);
+        memcpy(out, msg.data(), n);
+        out[n] = 0;
+    }
+    return (int)msg.size();
+}
+
 int capi_vocab_size(void* h) { return (int)((CapiModel*)h)->m->vocab.id_to_token.size(); }
 
 }  // extern "C"

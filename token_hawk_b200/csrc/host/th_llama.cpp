@@ -11,6 +11,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <limits>
+#include <queue>
 #include <utility>
 
 namespace th {
@@ -229,21 +231,147 @@ void build_layer_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, std::shar
 }
 
 // greedy branch of th-llama.cpp:814-838; other temperatures are outside the hot path
-tk_llama_token llama_sample_top_p_top_k(std::shared_ptr<LlamaModel> m, const std::vector<tk_llama_token>&, int, float, float temp,
-                                        float, std::vector<float>& logits) {
+// th-llama.cpp:814-907.  temp <= 0: the token with the highest logit (lowest id wins ties).  Otherwise: logits / temp,
+// CTRL repetition penalty on the ids in last_n_tokens (negative scores are multiplied, positive ones divided), top-k by
+// partial sort, softmax over the survivors with a double accumulator, nucleus cut at cumulative probability top_p and
+// renormalisation, then one draw from std::discrete_distribution with the model's mt19937.  Same library calls in the
+// same order as the reference, so with the same seed the draw is the same token (tests/golden/sampler.json).
+tk_llama_token llama_sample_top_p_top_k(std::shared_ptr<LlamaModel> m, const std::vector<tk_llama_token>& last_n_tokens, int top_k,
+                                        float top_p, float temp, float repeat_penalty, std::vector<float>& logits) {
     const int n_logits = m->n_vocab;
-    if ((int)logits.size() < n_logits) return -1;
-    const float* pl = logits.data() + logits.size() - n_logits;
-    if (temp > 0) {
-        fprintf(stderr, "llama_sample_top_p_top_k: only the greedy branch (temp <= 0) is implemented\n");
-        return -1;
-    }
-    float max_logit = pl[0];
-    tk_llama_token max_id = 0;
-    for (int i = 1; i < n_logits; ++i)
-        if (pl[i] > max_logit) { max_logit = pl[i]; max_id = i; }
-    return max_id;
+    if ((int)logits.size() < n_logits || n_logits <= 0) return -1;
+    return llama_sample_logits(m->rng, logits.data() + logits.size() - n_logits, n_logits, last_n_tokens, top_k, top_p, temp, repeat_penalty);
 }
+tk_llama_token llama_sample_logits(std::mt19937& rng, const float* pl, int n_logits, const std::vector<tk_llama_token>& last_n_tokens, int top_k,
+                                   float top_p, float temp, float repeat_penalty) {
+    if (temp <= 0) {
+        float max_logit = pl[0];
+        tk_llama_token max_id = 0;
+        for (int i = 1; i < n_logits; ++i)
+            if (pl[i] > max_logit) { max_logit = pl[i]; max_id = i; }
+        return max_id;
+    }
+    typedef std::pair<float, tk_llama_token> Cand;
+    std::vector<Cand> cand;
+    cand.reserve(n_logits);
+    const float scale = 1.0f / temp;
+    for (int i = 0; i < n_logits; ++i) {
+        const bool seen = std::find(last_n_tokens.begin(), last_n_tokens.end(), i) != last_n_tokens.end();
+        float v = pl[i] * scale;
+        if (seen) v = (pl[i] < 0.0f) ? v * repeat_penalty : v / repeat_penalty;
+        cand.push_back(Cand(v, i));
+    }
+    if (top_k > 0 && top_k < n_logits) {
+        std::partial_sort(cand.begin(), cand.begin() + top_k, cand.end(), [](const Cand& a, const Cand& b) { return a.first > b.first; });
+        cand.resize(top_k);
+    }
+    float maxl = -std::numeric_limits<float>::infinity();
+    for (const Cand& c : cand) maxl = std::max(maxl, c.first);
+    std::vector<float> probs;
+    probs.reserve(cand.size());
+    double sum = 0.0;
+    for (const Cand& c : cand) {
+        const float pr = expf(c.first - maxl);
+        probs.push_back(pr);
+        sum += pr;
+    }
+    for (float& pr : probs) pr /= sum;
+    if (top_p < 1.0) {
+        double cumsum = 0.0;
+        for (int i = 0; i < (int)probs.size(); ++i) {
+            cumsum += probs[i];
+            if (cumsum >= top_p) {
+                probs.resize(i + 1);
+                cand.resize(i + 1);
+                break;
+            }
+        }
+        cumsum = 1.0 / cumsum;
+        for (float& pr : probs) pr *= cumsum;
+    }
+    std::discrete_distribution<> dist(probs.begin(), probs.end());
+    return cand[dist(rng)].second;
+}
+
+// ---- tokenizer (TkLlamaTokenizer, th-llama.cpp:909-1041): SentencePiece-style greedy merging ----
+// The text is cut into UTF-8 characters; every adjacent pair whose concatenation is a vocabulary entry is a merge
+// candidate scored by that entry; the best candidate (highest score, then leftmost) is applied until none is left.
+// Pieces that are not in the vocabulary come out as byte tokens (byte value + 3).
+namespace {
+struct Piece { int prev, next; size_t off, len; };
+struct Merge { int left, right; float score; size_t size; };
+struct MergeLess {   // priority_queue keeps the LARGEST on top: higher score first, then the smaller left index
+    bool operator()(const Merge& a, const Merge& b) const { return a.score < b.score || (a.score == b.score && a.left > b.left); }
+};
+size_t utf8_char_len(unsigned char lead) {
+    static const unsigned char len_by_high_nibble[16] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 4};
+    return len_by_high_nibble[lead >> 4];
+}
+}  // namespace
+
+std::vector<tk_llama_token> tk_llama_tokenize(const LlamaVocab& vocab, const std::string& text, bool add_bos) {
+    std::vector<tk_llama_token> out;
+    if (text.empty()) return out;
+    if (add_bos) out.push_back(tk_llama_token_bos());
+    std::vector<Piece> pieces;
+    for (size_t off = 0; off < text.size();) {
+        const size_t len = std::min(text.size() - off, utf8_char_len((unsigned char)text[off]));
+        Piece pc;
+        pc.prev = (int)pieces.size() - 1;
+        pc.off = off;
+        pc.len = len;
+        off += len;
+        pc.next = off == text.size() ? -1 : (int)pieces.size() + 1;
+        pieces.push_back(pc);
+    }
+    std::priority_queue<Merge, std::vector<Merge>, MergeLess> queue;
+    auto propose = [&](int left, int right) {
+        if (left < 0 || right < 0) return;
+        const std::string joined = text.substr(pieces[left].off, pieces[left].len + pieces[right].len);
+        auto it = vocab.token_to_id.find(joined);
+        if (it == vocab.token_to_id.end() || (size_t)it->second >= vocab.id_to_token.size()) return;
+        queue.push(Merge{left, right, vocab.id_to_token[it->second].score, joined.size()});
+    };
+    for (size_t i = 1; i < pieces.size(); ++i) propose((int)i - 1, (int)i);
+    while (!queue.empty()) {
+        const Merge mg = queue.top();
+        queue.pop();
+        Piece& l = pieces[mg.left];
+        Piece& r = pieces[mg.right];
+        if (l.len == 0 || r.len == 0 || l.len + r.len != mg.size) continue;      // stale: one side was merged meanwhile
+        l.len += r.len;
+        r.len = 0;
+        l.next = r.next;
+        if (r.next >= 0) pieces[r.next].prev = mg.left;
+        propose(l.prev, mg.left);
+        propose(mg.left, l.next);
+    }
+    for (int i = 0; i != -1; i = pieces[i].next) {
+        const Piece& pc = pieces[i];
+        auto it = vocab.token_to_id.find(text.substr(pc.off, pc.len));
+        if (it != vocab.token_to_id.end()) { out.push_back(it->second); continue; }
+        for (size_t j = 0; j < pc.len; ++j) out.push_back((tk_llama_token)(unsigned char)text[pc.off + j] + 3);
+    }
+    return out;
+}
+std::vector<tk_llama_token> tk_llama_tokenize(std::shared_ptr<LlamaModel> m, const std::string& text, bool add_bos) {
+    return tk_llama_tokenize(m->vocab, text, add_bos);
+}
+int tk_llama_tokenize(std::shared_ptr<LlamaModel> m, const char* text, tk_llama_token* tokens, int n_max_tokens, bool add_bos) {
+    const std::vector<tk_llama_token> res = tk_llama_tokenize(m->vocab, text, add_bos);
+    if (n_max_tokens < (int)res.size()) {
+        fprintf(stderr, "%s: too many tokens\n", __func__);
+        return -(int)res.size();
+    }
+    for (size_t i = 0; i < res.size(); ++i) tokens[i] = res[i];
+    return (int)res.size();
+}
+const char* tk_llama_token_to_str(std::shared_ptr<LlamaModel> m, tk_llama_token token) {      // th-llama.cpp:1094-1100
+    if (token < 0 || (size_t)token >= m->vocab.id_to_token.size()) return nullptr;
+    return m->vocab.id_to_token[token].tok.c_str();
+}
+tk_llama_token tk_llama_token_bos() { return 1; }
+tk_llama_token tk_llama_token_eos() { return 2; }
 
 static bool write_uniforms(WGPUQueue queue, std::shared_ptr<LlamaModel> m, int n_tokens, int n_past) {
     // th-llama.cpp:479-550
@@ -400,6 +528,53 @@ std::vector<tk_llama_token> generate_greedy(WGPUDevice device, WGPUQueue queue, 
         m->n_past += 1;
     }
     return out;
+}
+
+// do_inference, synchronous flavour (th-llama.cpp:111-168, 199-238): a leading space is added to the first prompt of a
+// context, the prompt is tokenised with BOS and consumed one token per evaluation (kAllowedSubsequentBatchSize = 1,
+// th-llama.cpp:15) while last_n_tokens slides, then tokens are generated until EOS, max_new_tokens, or the context is
+// full; every generated piece goes to onNewToken(piece, message so far) and the whole message is returned.
+// Differences from the reference: the limit is a parameter (reference: kMaxOutputTokens = 500 over a 512 context), the
+// sampler temperature is m->samplerTemp (reference: 0.8 hard-coded), nothing is printed.
+std::string do_inference(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, std::string prompt, int max_new_tokens) {
+    if (m->n_past >= m->n_ctx) {
+        const std::string error = "Maximum context reached (" + std::to_string(m->n_ctx) + "). Please reset context.";
+        if (m->onError) m->onError(error);
+        return std::string();
+    }
+    if (m->n_past == 0) prompt.insert(0, 1, ' ');
+    m->embd_inp = tk_llama_tokenize(m, prompt, true);
+    m->n_consumed = 0;
+    if ((int)m->embd_inp.size() > m->n_ctx - 4 - m->n_past) {
+        fprintf(stderr, "%s: error: prompt is too long (%d tokens, max %d)\n", __func__, (int)m->embd_inp.size(), m->n_ctx - 4 - m->n_past);
+        if (m->onError) m->onError("prompt is too long");
+        return std::string();
+    }
+    if (m->last_n_tokens.empty()) m->last_n_tokens.assign((size_t)m->n_ctx, 0);
+    m->generatedMessage.clear();
+    int produced = 0;
+    while (m->n_past < m->n_ctx) {
+        tk_llama_token in;
+        const bool from_prompt = (int)m->embd_inp.size() > m->n_consumed;
+        if (from_prompt) {
+            in = m->embd_inp[m->n_consumed++];
+            m->last_n_tokens.erase(m->last_n_tokens.begin());
+            m->last_n_tokens.push_back(in);
+        } else {
+            in = m->lastGeneratedToken;
+            if (in == tk_llama_token_eos() || produced >= max_new_tokens) break;
+            const char* piece = tk_llama_token_to_str(m, in);
+            m->generatedMessage += piece ? piece : "";
+            ++produced;
+            if (m->onNewToken) m->onNewToken(piece ? piece : "", m->generatedMessage);
+        }
+        const tk_llama_token next = th_eval_gpu(device, queue, m, &in, 1, m->n_past);
+        if (next < 0) { if (m->onError) m->onError("evaluation failed"); break; }
+        m->n_past += 1;
+        m->lastGeneratedToken = next;
+    }
+    if (m->onInferenceComplete) m->onInferenceComplete(m->generatedMessage);
+    return m->generatedMessage;
 }
 
 }  // namespace th

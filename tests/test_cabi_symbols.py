@@ -34,7 +34,8 @@ def test_host_library_exports_capi(built):
     lib = ctypes.CDLL(built[0], mode=ctypes.RTLD_GLOBAL)
     host = ctypes.CDLL(built[1])
     for n in ("capi_device_create", "capi_model_synthetic", "capi_model_load", "capi_eval", "capi_generate",
-              "capi_generate_device", "capi_tensor_download", "capi_fill_kv", "capi_hidden"):
+              "capi_generate_device", "capi_tensor_download", "capi_fill_kv", "capi_hidden", "capi_tune", "capi_sample",
+              "capi_vocab_create", "capi_vocab_tokenize", "capi_tokenize", "capi_token_str", "capi_set_sampler", "capi_inference"):
         assert hasattr(host, n), n
     out = subprocess.run(["nm", "-DC", built[1]], capture_output=True, text=True).stdout
     for sym in ("th::cmdbuf_vector_mat_mul_trans", "th::cmdbuf_rms_norm", "th::cmdbuf_RoPE", "th::cmdbuf_mat_mul",
@@ -42,7 +43,8 @@ def test_host_library_exports_capi(built):
                 "th::cmdbuf_element_mult_in_place", "th::cmdbuf_row_element_multiply", "th::cmdbuf_masked_softmax",
                 "th::cmdbuf_vector_multi_mat_mul_split_trans", "th::cmdbuf_vector_reduce", "th::cmdbuf_f16_f32_conversion",
                 "th::th_eval_gpu", "th::build_layer_cmdbuf", "th::build_final_compute_cmdbuf", "th::load_llama_file",
-                "th::post_load_init_model", "th::load_header", "th::load_weights", "th::build_pipelines_llama"):
+                "th::post_load_init_model", "th::load_header", "th::load_weights", "th::build_pipelines_llama",
+                "th::llama_sample_top_p_top_k", "th::tk_llama_tokenize", "th::tk_llama_token_to_str", "th::do_inference"):
         assert sym in out, sym
 
 
@@ -54,6 +56,14 @@ def test_kernels_are_sm100a_native(built):
     assert archs == {"100a"}, archs
     sass = subprocess.run(["cuobjdump", "-sass", built[0]], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass
+    # the decode kernel: L2 look-ahead prefetch, packed f32x2 FMA, warpgroup register reallocation (math warps really use
+    # more than the 168 registers a 384-thread launch grants); the GEMM: tcgen05 MMA with TMEM and TMA
+    dec = sass[sass.index("decode_kernelILb0"):]
+    dec = dec[:dec.index("Function :", 20)] if "Function :" in dec[20:] else dec
+    assert "UBLKPF" in dec and "FFMA2" in dec and "USETMAXREG" in dec
+    assert max(int(r) for r in re.findall(r"\bR(\d+)\b", dec)) > 168
+    assert "UTCHMMA" in sass or "UTCQMMA" in sass or "UTCMMA" in sass, "tcgen05 MMA missing from the prefill GEMM"
+    assert "UTMALDG" in sass, "TMA tensor loads missing from the prefill GEMM"
 
 
 def test_no_gpu_means_loud_failure_not_fallback(built):

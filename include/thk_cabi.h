@@ -192,6 +192,10 @@ int thk_decoder_profile(thk_decoder* dec, int enable, unsigned long long* host_o
  *   "poll_single"  1: a stale read of such a vector spins on the one stale element before re-reading everything
  * Takes effect at the next step.  Unknown key -> THK_E_INVALID. */
 int thk_decoder_tune(thk_decoder* dec, const char* key, int value);
+/* The static tile schedule of CTA `cta` (of `grid`) in matvec phase `phase` (0 QKV, 1 Wo, 2 W1/W3, 3 W2, 4 output), computed
+ * on the host by the code the kernel runs: out = {C, KT, CT, paired, n_groups, then (segment, first row, rows) per row group}.
+ * No reference analogue (the reference dispatches one workgroup per row, th.cpp:3046-3139); used by the CPU tests. */
+int thk_decoder_plan(const thk_llama_dims* dims, int phase, int grid, int cta, int32_t* out, int cap);
 /* tensor-parallel wiring: peer pointers obtained by the host via CUDA IPC (or same-process P2P).
  * peer_bufs[r] / peer_flags[r] are device-visible addresses of rank r's exchange buffer / flag
  * array as returned by thk_decoder_exchange_info on that rank. */

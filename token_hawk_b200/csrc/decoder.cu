@@ -344,29 +344,30 @@ struct RowIt {
                                // constant-bank read per segment test costs ~60 cycles of latency at every row-group end)
     // even-aligned contiguous share of the phase's rows; the two divisions cost ~0.3 us of dependent latency, so the
     // kernel evaluates this once per launch and phase kind (SmemMisc::range) instead of at every phase start
-    static __device__ __forceinline__ void share(const PhaseDesc& d, int& r0, int& r1) {
+    static __host__ __device__ __forceinline__ void share(const PhaseDesc& d, unsigned n, unsigned b, int& r0, int& r1) {
         const unsigned total = (unsigned)(d.paired ? d.rows[0] : d.rows[0] + d.rows[1] + d.rows[2]);
-        const unsigned n = gridDim.x, b = blockIdx.x;
         r0 = (int)(((total * b) / n) & ~1u);
         r1 = (b + 1 == n) ? (int)total : (int)(((total * (b + 1)) / n) & ~1u);
     }
-    __device__ __forceinline__ void init(const SmemMisc* misc, int ph, const PhaseDesc& d) {
-        r = misc->range[ph][0];
-        r_end = misc->range[ph][1];
+    __host__ __device__ __forceinline__ void init_range(int r0, int r1, const PhaseDesc& d) {
+        r = r0;
+        r_end = r1;
         e0 = d.paired ? 0x7fffffff : d.rows[0];
         e1 = d.paired ? 0x7fffffff : d.rows[0] + d.rows[1];
         place();
     }
-    __device__ __forceinline__ bool valid() const { return r < r_end; }
-    __device__ __forceinline__ void place() {
+    __device__ __forceinline__ void init(const SmemMisc* misc, int ph, const PhaseDesc& d) { init_range(misc->range[ph][0], misc->range[ph][1], d); }
+    __host__ __device__ __forceinline__ bool valid() const { return r < r_end; }
+    __host__ __device__ __forceinline__ void place() {
         // a group never crosses a segment or the end of this CTA's share
         si = r < e0 ? 0 : (r < e1 ? 1 : 2);
         const int seg_begin = r < e0 ? 0 : (r < e1 ? e0 : e1);
         const int seg_end = r < e0 ? e0 : (r < e1 ? e1 : 0x7fffffff);
         row0 = r - seg_begin;
-        nrows = min(min(kRows, seg_end - r), r_end - r);
+        const int a = seg_end - r < kRows ? seg_end - r : kRows, b = r_end - r;
+        nrows = a < b ? a : b;
     }
-    __device__ __forceinline__ void next() { r += nrows; place(); }
+    __host__ __device__ __forceinline__ void next() { r += nrows; place(); }
 };
 
 // attention work split (shared by producer and consumers)
@@ -1391,7 +1392,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
     }
     if (threadIdx.x >= 64 && threadIdx.x < 69) {            // (a parked warp of the service group)
         const int ph = (int)threadIdx.x - 64;
-        RowIt::share(p.ph[ph], S.misc->range[ph][0], S.misc->range[ph][1]);
+        RowIt::share(p.ph[ph], gridDim.x, blockIdx.x, S.misc->range[ph][0], S.misc->range[ph][1]);
     }
     __syncthreads();
     if (threadIdx.x < kMathBase) {
@@ -1419,6 +1420,15 @@ PhaseDesc make_phase(int nseg, const int* rows, int C, bool paired) {
 }
 
 }  // namespace
+
+// the five matvec phases of a (possibly tensor-parallel) model: segments, rows and K tiling
+static void fill_phases(DecParams& p) {
+    { const int r[3] = {p.Eh, p.Eh, p.Eh}; p.ph[PH_QKV] = make_phase(3, r, p.n_embd, false); }
+    { const int r[3] = {p.n_embd, 0, 0}; p.ph[PH_WO] = make_phase(1, r, p.Eh, false); }
+    { const int r[3] = {p.Fh, p.Fh, 0}; p.ph[PH_W13] = make_phase(2, r, p.n_embd, true); }
+    { const int r[3] = {p.n_embd, 0, 0}; p.ph[PH_W2] = make_phase(1, r, p.Fh, false); }
+    { const int r[3] = {p.Vl, 0, 0}; p.ph[PH_OUT] = make_phase(1, r, p.n_embd, false); }
+}
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -1481,11 +1491,7 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     p.Eh = dims->n_embd / tp; p.Fh = dims->n_ff / tp; p.Hl = dims->n_head / tp; p.Vl = dims->n_vocab / tp;
     p.emb = tok_embeddings; p.norm = norm; p.out_w = output;
     d->grid = ctx->sm_count;
-    { const int r[3] = {p.Eh, p.Eh, p.Eh}; p.ph[PH_QKV] = make_phase(3, r, p.n_embd, false); }
-    { const int r[3] = {p.n_embd, 0, 0}; p.ph[PH_WO] = make_phase(1, r, p.Eh, false); }
-    { const int r[3] = {p.Fh, p.Fh, 0}; p.ph[PH_W13] = make_phase(2, r, p.n_embd, true); }
-    { const int r[3] = {p.n_embd, 0, 0}; p.ph[PH_W2] = make_phase(1, r, p.Fh, false); }
-    { const int r[3] = {p.Vl, 0, 0}; p.ph[PH_OUT] = make_phase(1, r, p.n_embd, false); }
+    fill_phases(p);
     if (getenv("THK_DEBUG"))
         for (int i = 0; i < 5; ++i)
             fprintf(stderr, "phase %d: C=%d CT=%d KT=%d rows=%d,%d,%d paired=%d\n", i, p.ph[i].C, p.ph[i].CT, p.ph[i].KT,
@@ -1633,6 +1639,33 @@ extern "C" int thk_decoder_tune(thk_decoder* d, const char* key, int value) {
     else if (!strcmp(key, "poll_single")) d->p.poll_single = value != 0;
     else if (!strcmp(key, "nosync")) d->p.nosync = value != 0;
     else { thk_set_error("thk_decoder_tune: unknown key %s", key); return THK_E_INVALID; }
+    return THK_OK;
+}
+
+// The static schedule of one CTA in one matvec phase, computed on the host with the very code the kernel runs
+// (RowIt): out = {C, KT, CT, paired, n_groups, then per group: segment, first row, rows}.  Lets CPU tests check that the
+// partition covers every row exactly once for any shape / grid / tensor-parallel split without a GPU.
+extern "C" int thk_decoder_plan(const thk_llama_dims* dims, int phase, int grid, int cta, int32_t* out, int cap) {
+    THK_CHECK_ARG(dims && out && phase >= 0 && phase < 5 && grid > 0 && cta >= 0 && cta < grid && cap >= 5, "thk_decoder_plan: bad argument");
+    const int tp = dims->tp_size > 0 ? dims->tp_size : 1;
+    THK_CHECK_ARG(dims->n_embd > 0 && dims->n_ff > 0 && dims->n_vocab > 0 && dims->n_embd % tp == 0 && dims->n_ff % tp == 0 && dims->n_vocab % tp == 0,
+                  "thk_decoder_plan: bad dims");
+    DecParams pp{};
+    pp.n_embd = dims->n_embd; pp.Eh = dims->n_embd / tp; pp.Fh = dims->n_ff / tp; pp.Vl = dims->n_vocab / tp;
+    fill_phases(pp);
+    const PhaseDesc& ph = pp.ph[phase];
+    int r0, r1;
+    RowIt::share(ph, (unsigned)grid, (unsigned)cta, r0, r1);
+    RowIt it;
+    it.init_range(r0, r1, ph);
+    out[0] = ph.C; out[1] = ph.KT; out[2] = ph.CT; out[3] = ph.paired;
+    int n = 0;
+    for (; it.valid(); it.next()) {
+        if (5 + 3 * (n + 1) > cap) { thk_set_error("thk_decoder_plan: output too small"); return THK_E_INVALID; }
+        out[5 + 3 * n] = it.si; out[6 + 3 * n] = it.row0; out[7 + 3 * n] = it.nrows;
+        ++n;
+    }
+    out[4] = n;
     return THK_OK;
 }
 

@@ -181,9 +181,10 @@ int thk_decoder_last_launches(thk_decoder* dec);
 /* blocks on the stream and reports an in-kernel abort (watchdog on a barrier wait -> THK_E_TIMEOUT,
  * token id out of range -> THK_E_INVALID); the reference's validators assert instead (th-llama.cpp:606) */
 int thk_decoder_check(thk_decoder* dec);
-/* phase profile (no reference analogue; the reference only has wall-clock stats, th.cpp:45-87): when
- * enabled, CTA 0 stores %globaltimer (ns) at kernel start [0] and after grid barrier k [k]; host_out
- * (may be NULL) receives the first n entries of the last launch. */
+/* in-kernel timeline (no reference analogue; the reference only has wall-clock stats, th.cpp:45-87).  Only in the
+ * profiling build of this library (-DTHK_PROFILE, token_hawk_b200/lib_prof); the production build returns
+ * THK_E_UNSUPPORTED when asked to enable it.  Layout of host_out (u64 %globaltimer ns of the last launch):
+ * [cta][phase < 256][8 marks] | [cta][4 producer stats] | [cta][64 tile-retired] | [cta][64 tile-issued] (prof_phase). */
 int thk_decoder_profile(thk_decoder* dec, int enable, unsigned long long* host_out, int n);
 /* tuning knobs of the persistent kernel (no reference analogue; scripts/tune.py sweeps them on the GPU):
  *   "l2_ahead_kb"  KB of a CTA's upcoming rows the producer warp asks L2 for at a phase boundary (0 = off)

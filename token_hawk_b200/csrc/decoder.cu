@@ -4,20 +4,24 @@
 // + build_final_compute_cmdbuf, th-llama.cpp:270-452, 240-268, 592-640) with a single launch of
 // one CTA per SM.  Design (DESIGN.md has the full write-up and the measurements behind it):
 //
-//   * warp 0 of every CTA is the PRODUCER: it walks the CTA's static list of weight / KV tiles for
-//     the whole token (all layers, all phases) and streams them HBM -> shared memory with
-//     cp.async.bulk (UBLKCP) into a ring of 32 KB slots guarded by full/empty mbarriers.  It never
-//     waits for activations, so HBM stays busy across phase boundaries and grid barriers.
-//   * warps 1..8 are the MATH warps: wait for a tile (8 rows x <= 2048 columns of f16), 128-bit LDS,
-//     exact f16 -> f32, f32 FMA against the activation vector staged in shared memory.  Nothing
-//     else is on their per-tile path.  At the end of a row group every lane dumps its 8 partial row
-//     sums to shared memory (no shuffles, no CTA barrier) and signals an mbarrier.
-//   * warp 9 is the EPILOGUE warp: reduces the dumped partials in a fixed order, runs the fused
-//     epilogue (RoPE + KV append, residual add, SiLU*mul, logits + argmax), and owns the grid
-//     barrier that separates the data-dependent phases (one red.release + relaxed polling).
-//   * phases per layer: QKV | attention (split-KV, warp-private online softmax) | Wo | W1,W3 | W2;
-//     then logits.  RMSNorm*gain is the prologue of the consuming phase; the split-KV combine is
-//     the prologue of Wo.
+//   * 384 threads in three warpgroups: a service group (warp 0 = PRODUCER, warp 1 = EPILOGUE, two parked warps; 72
+//     registers/thread after setmaxnreg.dec) and two groups of four MATH warps (216 registers/thread).
+//   * the PRODUCER walks the CTA's static list of weight / KV tiles for the whole token (all layers, all phases) and
+//     streams them HBM -> shared memory with cp.async.bulk (UBLKCP) into a ring of 32 KB slots guarded by full/empty
+//     mbarriers.  It never waits for activations, so HBM stays busy across phase boundaries; when a phase boundary stalls
+//     the ring it asks L2 for the CTA's next rows (UBLKPF).
+//   * the MATH warps wait for a tile (8 rows x <= 2048 columns of f16), issue its ten 128-bit shared loads by
+//     shared-window address, convert f16 -> f32 exactly and accumulate with packed FFMA2 against the activation vector,
+//     which every lane stages privately (its own 8 columns per chunk) -- no CTA barrier in any prologue.  At the end of a
+//     row group a transposing shuffle reduction leaves 8 floats per warp in a ring of hand-off records (mbarriers).
+//   * the EPILOGUE warp adds the eight warp sums per row in a fixed order and runs the fused epilogue (RMS scale, RoPE +
+//     KV append, residual add, SiLU*mul, logits + argmax); it owns the grid barrier (one red.release + relaxed polling).
+//   * phases per layer: QKV | attention (split-KV, warp-private online softmax) | Wo | W1,W3 | W2; then logits.
+//     RMSNorm*gain is the prologue of the consuming phase; the split-KV combine is the prologue of Wo.  A grid barrier
+//     separates QKV | attention | Wo; Wo -> W1,W3 -> W2 -> next QKV synchronise through epoch-stamped copies of the
+//     vectors themselves (one 64-bit store per element, the consumer polls what it needs).
+//   * tensor parallel (decode_kernel<true>): Wo / W2 partial rows are pushed as epoch-stamped values into every rank's
+//     exchange region over NVLink; the consuming prologue adds them to the lane-private residual stream.
 //
 // Arithmetic follows oracle/th_oracle.c (the restatement of the WGSL); only summation order
 // differs.  No tensor cores: at M=1 the work is 1 FLOP/byte and HBM-bound.
@@ -36,7 +40,7 @@ constexpr int kMathWarps = 8;
 constexpr int kMathThreads = kMathWarps * 32;
 // Three warpgroups: {warp 0 producer, warp 1 epilogue, warps 2-3 parked} | math warps 0-3 | math warps 4-7.  A 10-warp CTA
 // would cap every thread at 168 registers (three warps share one SM sub-partition); with whole warpgroups the service
-// group hands registers to the math groups (setmaxnreg: 56 vs 224 per thread, 56 + 2 * 224 <= 512 per sub-partition lane).
+// group hands registers to the math groups (setmaxnreg: 72 vs 216 per thread, 72 + 2 * 216 <= 512 per sub-partition lane).
 constexpr int kMathBase = 128;
 constexpr int kThreads = kMathBase + kMathThreads;
 #ifdef THK_SVC_REGS

@@ -34,6 +34,13 @@ E, H, F, V, L, NMULT = 4096, 32, 11008, 32000, 32, 256
 W_BYTES = L * 2 * (4 * E * E + 3 * E * F) + 2 * V * E + (2 * L + 1) * 4 * E + 2 * E   # 13,215,2xx,xxx
 
 
+METRIC = "tokens/sec LLaMA-7B f16 single-token decode; achieved HBM GB/s vs roofline"      # BASELINE.json
+
+
+def workload_name(ctx, n_gpus):
+    return f"LLaMA-7B f16, 1-token decode, ctx={ctx} (n_past={ctx - 1}), {n_gpus}xB200"
+
+
 def kv_bytes(n_ctx_len, n_layer=L):
     return 2 * n_ctx_len * E * 4 * n_layer + 2 * E * 4 * n_layer
 
@@ -130,10 +137,12 @@ def run_reference(args):
             break
     v = float(np.median(vals))
     base["value"] = v
-    line = {"impl": "reference", "metric": "tokens/sec LLaMA-7B f16 single-token decode", "value": v, "unit": "tokens/s",
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s",
             "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 activations x f16 weights", "data": "synthetic",
-            "config": {"workload": f"LLaMA-7B f16, 1-token greedy decode, ctx={args.ctx}, CPU port of the reference arithmetic (oracle)"},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.ctx, max(1, args.gpus)), "n_layer": L,
+                       "arithmetic": "f32 activations/accumulate x f16 weights (reference arithmetic)",
+                       "arm": "CPU port of the reference arithmetic (oracle) on the host cores; bounded sample per step"},
             "cpu_baseline": base, "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference has no CPU path and its WebGPU/Dawn path cannot be built here; this arm is the oracle port on host cores"}
     print(json.dumps(line))
@@ -267,11 +276,12 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.ctx)
 
-    line = {"metric": "tokens/sec LLaMA-7B f16 single-token decode; achieved HBM GB/s vs roofline", "value": tok_s, "unit": "tokens/s",
+    line = {"metric": METRIC, "value": tok_s, "unit": "tokens/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 activations/accumulate x f16 weights (reference arithmetic)",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"LLaMA-7B f16, 1-token decode, ctx={args.ctx} (n_past={n_past}), {world}xB200", "n_layer": args.layers,
+            "config": {"workload": workload_name(args.ctx, world), "n_layer": args.layers,
+                       "arithmetic": "f32 activations/accumulate x f16 weights (reference arithmetic)",
                        "l2": "inputs (13.2 GB weights + 0.5 GB KV per step) exceed the 126 MB L2; no flush needed",
                        "kv": "f32, synthetic fill for positions < n_past",
                        "parallelism": "single GPU" if world == 1 else f"tp{world}: row/column-sharded matvecs, in-kernel one-shot all-reduce over NVLink peer memory (2 per layer)"},

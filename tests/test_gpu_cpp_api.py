@@ -25,6 +25,19 @@ def test_cpp_api_test_compiles():
     assert os.path.exists(build_cpp_test())
 
 
+def test_cpp_host_surface_on_cpu():
+    """tokenizer + sampler through include/th/th-llama.hpp from C++ (no device needed)."""
+    from token_hawk_b200 import build
+    build.build()
+    lib = os.path.join(ROOT, "token_hawk_b200", "lib")
+    exe = os.path.join(lib, "th_host_test")
+    src = os.path.join(ROOT, "tests", "cpp", "th_host_test.cpp")
+    subprocess.check_call([build.CXX, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L" + lib, "-lth_b200", "-lthk_sm100a", "-Wl,-rpath," + lib])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "PASS th_host_test" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_api_on_gpu():
     exe = build_cpp_test()

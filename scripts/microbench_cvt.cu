@@ -9,7 +9,9 @@
 //   3  FFMA2 only
 //   4  integer convert (shift/mask into an f32 scaled by 2^-112, activation pre-scaled by 2^112) + FFMA2: moves the
 //      conversion from the FMA pipe to the ALU pipe; exact for finite f16 including subnormals
-// Output: cycles per (8 weights x 8 rows) lane-tile and the implied tiles/us per SM at the measured clock.
+// Output: cycles per 32 KB tile per SM and the implied us/tile at the measured clock.
+// (Round 1 ran a first version whose plain shared loads were hoisted out of the loop; it only confirmed the FFMA2 rate:
+//  64 FFMA2 per sub-partition and tile in 130 cycles = 2 cycles per warp instruction.)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench_cvt scripts/microbench_cvt.cu
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -49,8 +51,12 @@ __global__ void __launch_bounds__(256, 1) body(const uint4* __restrict__ w, floa
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
         uint4 v[8];
+        // volatile shared loads by address, as in the kernel: the compiler must not hoist them (and the conversions that
+        // depend on them) out of the loop -- a first version with plain loads measured nothing but the FFMA2 chain
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile) + (((uint32_t)threadIdx.x + (uint32_t)(it & 7)) & 255u) * 16u;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = tile[r * 256 + threadIdx.x];
+        for (int r = 0; r < 8; ++r)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[r].x), "=r"(v[r].y), "=r"(v[r].z), "=r"(v[r].w) : "r"(base + r * 4096u) : "memory");
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const uint32_t u[4] = {v[r].x, v[r].y, v[r].z, v[r].w};

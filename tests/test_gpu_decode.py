@@ -166,6 +166,49 @@ def test_error_behaviour(th, dev, oracle):
     g.close()
 
 
+def test_bad_device_token_aborts_cleanly(th, dev, oracle):
+    """A token id that only exists on the device (capi_step_async / thk_decoder_generate never see it on the host) and lies
+    outside the vocabulary: the kernel leaves before any phase starts, the status word surfaces as THK_E_INVALID, and the
+    context and the decoder keep working (ADVICE r1: the old abort path could fault the CUDA context)."""
+    cfg = oracle.TINY
+    g, o = make_pair(th, dev, oracle, cfg)
+    tok0, logits0 = g.eval([5], 0)
+    for bad in (cfg.n_vocab, -3, 1 << 30):
+        g.set_token(bad)
+        g.step_async(1)
+        with pytest.raises(th.ThkError) as e:
+            g.check()
+        assert e.value.code == th.THK_E_INVALID, e.value
+    g.check()                                                   # the status word was cleared
+    ref0 = o.eval([5], 0)
+    tok, logits = g.eval([7], 1)                                # the same context continues, KV row 0 is intact
+    ref = o.eval([7], 1)
+    assert rel(logits0, ref0) < 5e-5 and rel(logits, ref) < 5e-5 and tok == oracle.greedy(ref)
+    g.close()
+
+
+def test_watchdog_timeout_returns_error_not_a_dead_context(th, dev, oracle):
+    """Tensor-parallel decoder with a peer that never answers (its exchange region is mapped but no second rank runs): the
+    in-kernel watchdog must end the launch, thk_decoder_check must return THK_E_TIMEOUT, and the CUDA context must stay
+    usable -- the producer stops issuing copies once the status word is set (VERDICT r1 weak #8)."""
+    cfg = oracle.TINY
+    a = th.LlamaModel.synthetic(dev, cfg.n_vocab, cfg.n_embd, cfg.n_mult, cfg.n_head, cfg.n_layer, cfg.n_ctx, tp_rank=0, tp_size=2)
+    b = th.LlamaModel.synthetic(dev, cfg.n_vocab, cfg.n_embd, cfg.n_mult, cfg.n_head, cfg.n_layer, cfg.n_ctx, tp_rank=1, tp_size=2)
+    ptrs = [a.exchange_info()[0], b.exchange_info()[0]]
+    a.set_peers(ptrs); b.set_peers(ptrs)
+    a.tune("timeout_ms", 200)
+    a.set_token(3)
+    a.step_async(0)                                             # rank 1 is never launched: rank 0 waits for its partials
+    with pytest.raises(th.ThkError) as e:
+        a.check()
+    assert e.value.code == th.THK_E_TIMEOUT, e.value
+    a.close(); b.close()
+    g, o = make_pair(th, dev, oracle, cfg)                      # same device, same context: still healthy
+    tok, logits = g.eval([5], 0)
+    assert rel(logits, o.eval([5], 0)) < 5e-5
+    g.close()
+
+
 def test_loader_roundtrip_ggjt_file(th, dev, oracle, tmp_path):
     """oracle writes a ggjt v1 file (accepted by the reference's own loader, see test_oracle.py);
     the CUDA loader reads it; tensors and logits must agree."""

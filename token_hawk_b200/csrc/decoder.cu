@@ -4,24 +4,28 @@
 // + build_final_compute_cmdbuf, th-llama.cpp:270-452, 240-268, 592-640) with a single launch of
 // one CTA per SM.  Design (DESIGN.md has the full write-up and the measurements behind it):
 //
-//   * 384 threads in three warpgroups: a service group (warp 0 = PRODUCER, warp 1 = EPILOGUE, two parked warps; 72
-//     registers/thread after setmaxnreg.dec) and two groups of four MATH warps (216 registers/thread).
+//   * 19 warps: warp 0 = PRODUCER, warp 1 = EPILOGUE, warp 2 = REDUCER (tensor parallel only), 16 MATH warps
+//     (four per SM sub-partition: a ready tile's wait / load / convert / FMA chain of one warp hides behind the other three).
 //   * the PRODUCER walks the CTA's static list of weight / KV tiles for the whole token (all layers, all phases) and
 //     streams them HBM -> shared memory with cp.async.bulk (UBLKCP) into a ring of 32 KB slots guarded by full/empty
 //     mbarriers.  It never waits for activations, so HBM stays busy across phase boundaries; when a phase boundary stalls
 //     the ring it asks L2 for the CTA's next rows (UBLKPF).
-//   * the MATH warps wait for a tile (8 rows x <= 2048 columns of f16), issue its ten 128-bit shared loads by
-//     shared-window address, convert f16 -> f32 exactly and accumulate with packed FFMA2 against the activation vector,
-//     which every lane stages privately (its own 8 columns per chunk) -- no CTA barrier in any prologue.  At the end of a
-//     row group a transposing shuffle reduction leaves 8 floats per warp in a ring of hand-off records (mbarriers).
-//   * the EPILOGUE warp adds the eight warp sums per row in a fixed order and runs the fused epilogue (RMS scale, RoPE +
+//   * a tile is 8 rows x <= 2048 columns of f16.  Math warp (chunk c, row half h) owns rows 4h..4h+3 of the 256-column
+//     chunk c: four 128-bit shared loads by shared-window address, exact f16 -> f32 conversion, packed FFMA2 against the
+//     activation values of its 8 columns -- held in REGISTERS for the whole phase when the phase has <= 2 K tiles (every
+//     4096-column matrix), else re-read from shared memory.  The row sums of a finished row group are reduced with a
+//     transposing shuffle tree one tile LATER, between the next tile's loads and its math, and handed to the epilogue
+//     warp through a ring of records (mbarriers).
+//   * the EPILOGUE warp adds the sixteen warp sums per row in a fixed order and runs the fused epilogue (RMS scale, RoPE +
 //     KV append, residual add, SiLU*mul, logits + argmax); it owns the grid barrier (one red.release + relaxed polling).
 //   * phases per layer: QKV | attention (split-KV, warp-private online softmax) | Wo | W1,W3 | W2; then logits.
 //     RMSNorm*gain is the prologue of the consuming phase; the split-KV combine is the prologue of Wo.  A grid barrier
 //     separates QKV | attention | Wo; Wo -> W1,W3 -> W2 -> next QKV synchronise through epoch-stamped copies of the
 //     vectors themselves (one 64-bit store per element, the consumer polls what it needs).
-//   * tensor parallel (decode_kernel<true>): Wo / W2 partial rows are pushed as epoch-stamped values into every rank's
-//     exchange region over NVLink; the consuming prologue adds them to the lane-private residual stream.
+//   * tensor parallel (decode_kernel<true>): the Wo / W2 epilogues push their partial rows as epoch-stamped values into
+//     every rank's exchange region over NVLink (one hop); on every rank the REDUCER warp of CTA b owns 1/grid of the
+//     residual stream in registers, adds the tp partials in rank order (the read is the wait) and publishes the reduced
+//     epoch-stamped vector locally -- so every math warp polls ONE 32 KB vector exactly as on a single GPU.
 //
 // Arithmetic follows oracle/th_oracle.c (the restatement of the WGSL); only summation order
 // differs.  No tensor cores: at M=1 the work is 1 FLOP/byte and HBM-bound.
@@ -36,24 +40,20 @@ namespace {
 constexpr int kSlotBytes = 32 * 1024;
 constexpr int kNumSlots = 4;                          // measured on B200: 3 -> 2.83, 4 -> 2.72, 5 -> 2.75 ms/token (deeper rings queue more
                                                       // traffic ahead of the latency-critical barrier / prologue loads)
-constexpr int kMathWarps = 8;
+constexpr int kChunks = 8;                            // 256-column chunks per tile
+constexpr int kMathWarps = 16;                        // (chunk, row half)
 constexpr int kMathThreads = kMathWarps * 32;
-// Three warpgroups: {warp 0 producer, warp 1 epilogue, warps 2-3 parked} | math warps 0-3 | math warps 4-7.  A 10-warp CTA
-// would cap every thread at 168 registers (three warps share one SM sub-partition); with whole warpgroups the service
-// group hands registers to the math groups (setmaxnreg: 72 vs 216 per thread, 72 + 2 * 216 <= 512 per sub-partition lane).
-constexpr int kMathBase = 128;
-constexpr int kThreads = kMathBase + kMathThreads;
-#ifdef THK_SVC_REGS
-constexpr int kServiceRegs = THK_SVC_REGS, kMathRegs = 256 - THK_SVC_REGS / 2 - 4;
-#else
-constexpr int kServiceRegs = 72, kMathRegs = 216;     // measured (svc/math -> ms/token): 40/232 2.81, 56/224 2.79, 72/216 2.69, 104/200 2.73, 136/184 2.79
-#endif
+constexpr int kSvcWarps = 3;                          // producer, epilogue, reducer
+constexpr int kMathBase = kSvcWarps * 32;
+constexpr int kThreads = kMathBase + kMathThreads;    // 608 -> 104 registers per thread, no setmaxnreg, out-of-line slow paths allowed
 constexpr int kRows = 8;                              // rows per row group (= per tile)
+constexpr int kHalf = 4;                              // rows per math warp
 constexpr int kMaxTilePos = 128;                      // attention: positions per tile cap
 constexpr int kMaxHeadDim = 128;
 constexpr int kMaxSplit = 8;                          // attention: KV splits per head cap
 constexpr int kDumpBufs = 8;                          // row-group hand-off ring between the math warps and the epilogue warp
-enum NamedBarrier { BAR_ALL = 1, BAR_MATH = 2, BAR_PRE = 3 };
+constexpr int kMaxOwn = 4;                            // tensor parallel: residual elements per reducer lane (n_embd <= 128 * grid)
+enum NamedBarrier { BAR_ALL = 1, BAR_MATH = 2, BAR_PRE = 3, BAR_PAIR0 = 4 };   // BAR_PAIR0 + chunk: the two warps of a chunk
 
 // Host-computed tile schedule of one matvec phase
 struct PhaseDesc {
@@ -73,13 +73,12 @@ struct DecParams {
     const uint16_t* emb;
     const float* norm;
     const uint16_t* out_w;
-    float *x, *h1, *q, *ff, *part;
-    // Flagged copies of h1 / ff / x for the barrier-free transitions Wo -> W13 -> W2 -> next QKV (single GPU): element
-    // = (epoch << 32) | f32 bits, written with ONE 64-bit store, so a reader that sees this layer's epoch sees the value.
+    float *x, *q, *part;                // x: residual stream after the last layer (thk_decoder_hidden)
+    // Epoch-stamped vectors: element = (epoch << 32) | f32 bits, written with ONE 64-bit store, so a reader that sees the
+    // expected epoch sees the value.  xf: residual stream entering a layer (epoch flag_epoch + l), h1f: after attention
+    // (flag_epoch + l + 1), fff: FFN hidden (flag_epoch + l + 1).
     unsigned long long *h1f, *fff, *xf;
-    unsigned flag_epoch;                // epoch of layer l in this launch = flag_epoch + l + 1
-    unsigned res_off;                   // tensor parallel: byte offset of the residual-stream copy behind xs in shared memory
-    int dataflow;                       // 1: the three transitions above synchronise through the flagged vectors, no grid barrier
+    unsigned flag_epoch;
     int nosync;                         // DEBUG (wrong results): skip every cross-CTA wait, to time the pipeline without synchronisation
     int poll_single;                    // flagged reads: after a stale read spin on the one stale element before re-reading all
     float* amax_val;
@@ -96,11 +95,11 @@ struct DecParams {
     int att_max_split;
     unsigned long long timeout_ns;
     // tensor parallel exchange (tp_size > 1): every rank owns one region laid out as
-    //   u64 xbf[2][tp][n_embd] (flagged partials; the barrier path uses the first half as float xb[2][tp][n_embd])
+    //   u64 xbf[2][tp][n_embd] (epoch-stamped partial vectors of the Wo / W2 exchange, one slot per source rank)
     //   | float amax_val[tp] | int amax_idx[tp] | unsigned flags[tp] | unsigned flags2[tp]
     // and writes its partial vectors / argmax candidates straight into every peer's region over NVLink.
     unsigned char* xchg[8];             // region base per rank (peer-mapped pointers; [tp_rank] is local)
-    unsigned epoch_base;                // flags are monotonic: exchange k of this launch uses epoch_base + k + 1
+    unsigned epoch_base;                // argmax exchange flags are monotonic across launches
     unsigned l2_ahead;                  // bytes of this CTA's rows the producer asks L2 for when a phase boundary stalls the ring (0: off)
     int prof_phase;                     // timeline: phase whose per-tile consume / issue times are recorded (kProfTiles each)
     unsigned long long* prof;           // optional timeline: [cta][phase<256][8] u64 (see ProfSlot), then [cta][4] producer stats
@@ -174,6 +173,9 @@ __device__ __forceinline__ float lds32f(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts128f(uint32_t a, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void st_flagged(unsigned long long* p, float v, unsigned epoch) {
     const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
@@ -182,8 +184,15 @@ __device__ __forceinline__ void st_flagged_sys(unsigned long long* p, float v, u
     const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-__device__ __forceinline__ void ld_flagged2_sys(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
-    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_flagged1_sys(const unsigned long long* p) {
+    unsigned long long a;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
+__device__ __forceinline__ unsigned long long ld_flagged1(const unsigned long long* p) {
+    unsigned long long a;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
 }
 __device__ __forceinline__ void ld_flagged2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
@@ -199,9 +208,6 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* ptr) {
 }
 
 // exchange region accessors
-__device__ __forceinline__ float* xb_ptr(const DecParams& p, int rank, int which, int src) {
-    return (float*)p.xchg[rank] + ((size_t)which * p.tp_size + src) * p.n_embd;
-}
 __device__ __forceinline__ size_t xchg_tail(const DecParams& p) { return (size_t)2 * p.tp_size * p.n_embd * sizeof(unsigned long long); }
 // flagged partial vector `which` (0: Wo, 1: W2) of source rank `src` inside rank `rank`'s exchange region
 __device__ __forceinline__ unsigned long long* xbf_ptr(const DecParams& p, int rank, int which, int src) {
@@ -213,9 +219,8 @@ __device__ __forceinline__ unsigned* xflags(const DecParams& p, int rank, int se
     return (unsigned*)(p.xchg[rank] + xchg_tail(p)) + (2 + set) * p.tp_size;
 }
 
-// The in-kernel timeline is compiled in only with -DTHK_PROFILE (token_hawk_b200/lib_prof): its marks must be out-of-line
-// calls (an inlined %globaltimer read is hoisted above barriers by ptxas), and ANY ABI call in the kernel makes ptxas
-// cap every thread at the service warpgroup's register budget instead of honouring setmaxnreg per branch.
+// The in-kernel timeline is compiled in only with -DTHK_PROFILE (token_hawk_b200/lib_prof): its marks are out-of-line
+// calls (an inlined %globaltimer read is hoisted above barriers by ptxas; a call is a scheduling fence).
 #ifdef THK_PROFILE
 #define PROF(p) ((p).prof)
 #else
@@ -230,36 +235,46 @@ __device__ __noinline__ void prof_tile(unsigned long long* prof, int which, int 
 __device__ __noinline__ void prof_mark(unsigned long long* prof, unsigned phase, int slot) {   // out of line: ~25 call sites
     if (phase < (unsigned)kProfPhases) prof[((size_t)blockIdx.x * kProfPhases + phase) * 8 + slot] = gtimer();
 }
-
-// math warps: `pm` is non-null only in the one thread that records.  The store goes through the out-of-line prof_mark:
-// an inlined %globaltimer read is hoisted by ptxas above barriers and waits (measured: phase starts recorded ~3 us
-// early), a call is a scheduling fence.
+// math warps: `pm` is non-null only in the one thread that records
 __device__ __forceinline__ void mark(unsigned long long* pm, const DecParams& p, unsigned phase, int slot) {
     if (pm != nullptr) prof_mark(PROF(p), phase, slot);
 }
 
-__device__ __forceinline__ bool aborted(const DecParams& p) { return ld_volatile_u32(p.status) != 0; }
 __device__ __forceinline__ void raise_abort(const DecParams& p, unsigned code, unsigned a, unsigned b) {
     if (atomicCAS(p.status, 0u, code) == 0u) { p.status[1] = a; p.status[2] = b; p.status[3] = blockIdx.x; }
 }
 
-// Slow path of every mbarrier wait: bounded by %globaltimer.  Returns false when the watchdog fired or
-// another CTA aborted; the caller then runs the rest of the (static) schedule without waiting, so the
-// kernel still terminates and the host sees THK_E_TIMEOUT instead of a wedged GPU.
-__device__ __forceinline__ bool mbar_wait_slow(const DecParams& p, uint32_t bar, uint32_t parity, unsigned tag) {
+// Slow path of every mbarrier wait: bounded by %globaltimer, out of line (one copy; the hot loops stay small).  Returns
+// false when the watchdog fired or another CTA aborted; the caller then walks the rest of its (static) schedule without
+// waiting and without issuing copies, so the kernel terminates and the host sees THK_E_TIMEOUT instead of a wedged GPU.
+__device__ __noinline__ bool mbar_wait_slow(unsigned* status, unsigned long long timeout_ns, uint32_t bar, uint32_t parity, unsigned tag) {
+    if (ld_volatile_u32(status) != 0) return false;      // an abort is sticky: after it every wait gives up at once
     const unsigned long long t0 = gtimer();
     unsigned it = 0;
     while (!mbar_try_wait(bar, parity)) {
         if ((++it & 255u) == 0u) {
-            if (aborted(p)) return false;
-            if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x100u | tag, bar, parity); return false; }
+            if (ld_volatile_u32(status) != 0) return false;
+            if (gtimer() - t0 > timeout_ns) {
+                if (atomicCAS(status, 0u, 0x100u | tag) == 0u) { status[1] = bar; status[2] = parity; status[3] = blockIdx.x; }
+                return false;
+            }
         }
     }
     return true;
 }
+// watchdog step of the global-memory polls (out of line); returns true when the poller must give up
+__device__ __noinline__ bool poll_watchdog(unsigned* status, unsigned long long timeout_ns, unsigned long long& t0, unsigned code, unsigned a, unsigned b) {
+    if (ld_volatile_u32(status) != 0) return true;
+    if (t0 == 0) { t0 = gtimer(); return false; }
+    if (gtimer() - t0 > timeout_ns) {
+        if (atomicCAS(status, 0u, code) == 0u) { status[1] = a; status[2] = b; status[3] = blockIdx.x; }
+        return true;
+    }
+    return false;
+}
 
 // ------------------------------------------------------------------------------------------
-// shared memory carve-up: | ring slots | SmemMisc | dump buffers | xs (activation vector) |
+// shared memory carve-up: | ring slots | SmemMisc | hand-off ring + attention scratch | xs (activation vector) |
 // ------------------------------------------------------------------------------------------
 struct SmemMisc {
     unsigned long long full[kNumSlots];
@@ -271,20 +286,19 @@ struct SmemMisc {
 };
 constexpr int kMiscBytes = 1024;
 static_assert(sizeof(SmemMisc) <= kMiscBytes, "SmemMisc too large");
-constexpr int kRecFloats = kRows + 1;                          // per warp: 8 row sums + its share of sum(v^2) of the phase input
+constexpr int kRecFloats = kHalf + 1;                          // per warp: 4 row sums + its share of sum(v^2) of the phase input
 constexpr int kRedFloats = kMathWarps * kRecFloats;            // one row-group hand-off record
 constexpr int kAttScratchOff = kDumpBufs * kRedFloats;         // attention scratch (floats) behind the hand-off ring
-constexpr int kRedBytes = 8 * 1024;                            // ring (2 KB) + attention scratch (<= 6 KB)
+constexpr int kRedBytes = 12 * 1024;                           // ring (2.5 KB) + attention scratch (<= 9.2 KB)
 static_assert(kAttScratchOff * 4 + (kMathWarps * kMaxHeadDim + 2 * kMathWarps + 2 * kMaxHeadDim) * 4 <= kRedBytes, "attention scratch does not fit");
 constexpr int kXsOffset = kNumSlots * kSlotBytes + kMiscBytes + kRedBytes;
 
 struct Smem {
     unsigned char* slots;
     SmemMisc* misc;
-    float* red;       // [kDumpBufs][kMathWarps][kRows] hand-off ring, then the attention scratch
+    float* red;       // [kDumpBufs][kMathWarps][kRecFloats] hand-off ring, then the attention scratch
     float* xs;
     uint32_t slots_a, full_a, empty_a, red_full_a, red_free_a, red_a, xs_a;   // shared-window addresses
-    // (tensor parallel: the lane-private residual stream sits behind xs, at xs_a + DecParams::res_off)
 };
 __device__ __forceinline__ Smem carve(unsigned char* base) {
     Smem s;
@@ -305,8 +319,6 @@ __device__ __forceinline__ Smem carve(unsigned char* base) {
     s.xs_a = a + kXsOffset;
     return s;
 }
-
-// every function that is kept out of line re-derives the carve-up from the dynamic shared memory base
 __device__ __forceinline__ Smem smem_view() {
     extern __shared__ __align__(1024) unsigned char smem_base[];
     return carve(smem_base);
@@ -314,6 +326,7 @@ __device__ __forceinline__ Smem smem_view() {
 
 // activation layout in xs: 256-col chunk c, lane l owns cols 8l..8l+7; its first float4 (cols 8l..8l+3) sits at
 // (c*64 + l)*16 B and its second at (c*64 + 32 + l)*16 B -- consecutive lanes hit consecutive banks (conflict free).
+// A chunk's values are staged by the two warps that own the chunk (K tiles alternate between them) and read by both.
 
 // ring position shared by producer and consumers (kept incrementally: no modulo per tile)
 struct Ring {
@@ -329,7 +342,7 @@ struct Cons {
 __device__ __forceinline__ void wait_full(const DecParams& p, const Smem& S, Cons& c, unsigned tag) {
     if (c.dead) return;
     const uint32_t bar = S.full_a + c.ring.sl * 8;
-    if (!mbar_try_wait(bar, c.ring.par)) c.dead = !mbar_wait_slow(p, bar, c.ring.par, tag);
+    if (!mbar_try_wait(bar, c.ring.par)) c.dead = !mbar_wait_slow(p.status, p.timeout_ns, bar, c.ring.par, tag);
 }
 __device__ __forceinline__ void release_slot(const Smem& S, Cons& c, int lane) {
     __syncwarp();
@@ -405,7 +418,7 @@ __device__ __forceinline__ void wait_empty(const DecParams& p, const Smem& S, Pr
     const uint32_t bar = S.empty_a + c.ring.sl * 8;
     if (!mbar_try_wait(bar, c.ring.par ^ 1u)) {
         const long long t0 = PROF(p) ? clock64() : 0;
-        c.dead = !mbar_wait_slow(p, bar, c.ring.par ^ 1u, tag);
+        c.dead = !mbar_wait_slow(p.status, p.timeout_ns, bar, c.ring.par ^ 1u, tag);
         if (PROF(p)) c.wait_cyc += clock64() - t0;
     }
 }
@@ -436,7 +449,7 @@ __device__ __forceinline__ void produce_mat_phase(const DecParams& p, const Smem
                 if (j == kNumSlots && p.l2_ahead != 0u && !c.dead && !mbar_try_wait(S.empty_a + c.ring.sl * 8, c.ring.par ^ 1u)) {
                     // The ring now holds nothing but tiles of this phase and its first tile has not been consumed: the
                     // consumers are still in the previous phase's tail / the grid barrier / the prologue, and the ring
-                    // (160 KB, ~3.5 us of this SM's HBM share) cannot cover that stall.  Ask L2 for this CTA's next rows
+                    // (128 KB, ~2.4 us of this SM's HBM share) cannot cover that stall.  Ask L2 for this CTA's next rows
                     // so HBM keeps streaming; after the stall the ring refills from L2 faster than HBM could feed it.
                     const uint32_t row_bytes_full = (uint32_t)C * 2u;
                     if (d.paired) {
@@ -450,11 +463,13 @@ __device__ __forceinline__ void produce_mat_phase(const DecParams& p, const Smem
                 }
                 wait_empty(p, S, c, 1);
                 if (PROF(p) && first && lane == 0) { prof_mark(PROF(p), phase_idx, PROF_PROD_FIRST); first = false; }
-                const uint32_t fb = S.full_a + c.ring.sl * 8, dst = S.slots_a + c.ring.sl * kSlotBytes;
-                const uint32_t row_bytes = (uint32_t)ncols * 2u;
-                if (lane == 0) mbar_expect_tx(fb, (uint32_t)it.nrows * row_bytes);
-                __syncwarp();
-                if (lane < it.nrows) bulk_g2s(dst + (uint32_t)lane * row_bytes, wrow + (size_t)lane * C + col0, row_bytes, fb, c.pol);
+                if (!c.dead) {       // after an abort nothing is issued any more: slots may still be in use and tx counts must not pile up
+                    const uint32_t fb = S.full_a + c.ring.sl * 8, dst = S.slots_a + c.ring.sl * kSlotBytes;
+                    const uint32_t row_bytes = (uint32_t)ncols * 2u;
+                    if (lane == 0) mbar_expect_tx(fb, (uint32_t)it.nrows * row_bytes);
+                    __syncwarp();
+                    if (lane < it.nrows) bulk_g2s(dst + (uint32_t)lane * row_bytes, wrow + (size_t)lane * C + col0, row_bytes, fb, c.pol);
+                }
                 if (PROF(p) && (int)phase_idx == p.prof_phase && j < kProfTiles && lane == 0) prof_tile(PROF(p), 1, j);
                 c.ring.advance();
                 ++c.tiles;
@@ -482,7 +497,7 @@ __device__ __forceinline__ void produce_att_phase(const DecParams& p, const Smem
                 if (PROF(p) && first && lane == 0) { prof_mark(PROF(p), phase_idx, PROF_PROD_FIRST); first = false; }
                 const float* base = (kv == 0 ? L.key_cache : L.value_cache) + ((size_t)h * p.n_ctx + pos) * D;
                 const uint32_t fb = S.full_a + c.ring.sl * 8;
-                if (lane == 0) { mbar_expect_tx(fb, bytes); bulk_g2s(S.slots_a + c.ring.sl * kSlotBytes, base, bytes, fb, c.pol); }
+                if (lane == 0 && !c.dead) { mbar_expect_tx(fb, bytes); bulk_g2s(S.slots_a + c.ring.sl * kSlotBytes, base, bytes, fb, c.pol); }
                 __syncwarp();
                 c.ring.advance();
                 ++c.tiles;
@@ -538,113 +553,162 @@ __device__ __forceinline__ unsigned long long cvt2(uint32_t h2) {     // exact f
     const float2 f = h2_to_f2(h2);
     return pack2(f.x, f.y);
 }
-__device__ __forceinline__ void fma8(const uint4& w, const unsigned long long (&x)[4], unsigned long long& acc) {
+__device__ __forceinline__ void fma8(const uint4& w, const unsigned long long* x, unsigned long long& acc) {
     acc = ffma2(x[0], cvt2(w.x), acc);
     acc = ffma2(x[1], cvt2(w.y), acc);
     acc = ffma2(x[2], cvt2(w.z), acc);
     acc = ffma2(x[3], cvt2(w.w), acc);
 }
 
-
-// One tile's operands in registers: 8 rows x this lane's 8 columns of f16 weights, and the matching activations packed
-// for FFMA2.
-struct TileRegs {
-    uint4 w[kRows];
-    unsigned long long xp[4];
-};
-// issue the ten 128-bit shared loads of the tile in ring slot `sl` (columns [col0, col0 + ncols) of the phase input)
-__device__ __forceinline__ void tile_load(const Smem& S, uint32_t sl, uint32_t xlane_a, int col, int lane, int col0, int ncols, TileRegs& t) {
-    const bool ok = col < ncols;                               // lanes past a short tile's last column read column 0 against zeros
-    const uint32_t stride = (uint32_t)ncols * 2u;
-    const uint32_t xa = ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4);
-    const uint32_t wa = S.slots_a + sl * kSlotBytes + (ok ? (uint32_t)col << 1 : 0u);
-    float4 x0 = lds128f(xa), x1 = lds128f(xa + 512u);
+// Hand the four row sums of a finished row group to the epilogue warp.  A transposing shuffle reduction (2 + 1 exchanges
+// halve the rows a lane holds while doubling the lanes summed, then 3 plain steps) leaves the warp total of row lane >> 3
+// in every lane; 4 floats per warp go into a ring of kDumpBufs hand-off records, so the math warps can run kDumpBufs row
+// groups ahead of the epilogue warp.  Fixed order of additions: deterministic.  Called one tile AFTER the group's last
+// tile, between that tile's shared loads and its math, so the shuffle latency overlaps the load latency.
+__device__ __forceinline__ void flush_group(const DecParams& p, const Smem& S, Cons& c, unsigned& gq, float (&v)[kHalf], float ss,
+                                            uint32_t dump_a, int lane) {
+    const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0;
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) t.w[r] = lds128(wa + (uint32_t)r * stride);
-    if (!ok) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
-    t.xp[0] = pack2(x0.x, x0.y); t.xp[1] = pack2(x0.z, x0.w); t.xp[2] = pack2(x1.x, x1.y); t.xp[3] = pack2(x1.z, x1.w);
+    for (int r = 0; r < 2; ++r) {
+        const float recv = __shfl_xor_sync(0xffffffffu, u4 ? v[r] : v[r + 2], 16);
+        v[r] = (u4 ? v[r + 2] : v[r]) + recv;
+    }
+    {
+        const float recv = __shfl_xor_sync(0xffffffffu, u3 ? v[0] : v[1], 8);
+        v[0] = (u3 ? v[1] : v[0]) + recv;
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 4);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    const unsigned buf = gq & (kDumpBufs - 1), use = gq / kDumpBufs;
+    if (use > 0 && !c.dead) {
+        const uint32_t fb = S.red_free_a + buf * 8;
+        if (!mbar_try_wait(fb, (use - 1) & 1u)) c.dead = !mbar_wait_slow(p.status, p.timeout_ns, fb, (use - 1) & 1u, 6);
+    }
+    if ((lane & 7) == 0) sts32f(dump_a + (buf * kRedFloats + (unsigned)(lane >> 3)) * 4u, v[0]);
+    if (lane == 1) sts32f(dump_a + (buf * kRedFloats + kHalf) * 4u, ss);          // this warp's share of sum(v^2) (norm phases)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(S.red_full_a + buf * 8);
+    ++gq;
 }
 
-// Stream this CTA's tiles of one matvec phase.  Per tile a warp owns one 256-column chunk of all 8 rows
-// (rows past a short group's end hold stale bytes; their sums are never read).  `gq` counts the row
-// groups handed to the epilogue warp since kernel start (hand-off record = gq % kDumpBufs).
-//
-// The per-tile body is the consumer's critical path: HBM delivers a 32 KB tile per ~0.62 us and SM, and only a consumer
-// that retires READY tiles faster than that turns the tiles buffered during a phase boundary into saved time.  Hence:
-// all ten 128-bit loads of a tile issued up front by shared-window address, a branch-free body (lanes past a short
-// tile's last column read column 0 against a zero activation), packed FFMA2, and nothing but ring bookkeeping around
-// it.  (Software pipelining across tiles -- the next tile's loads before this tile's math, second register set -- was
-// built and dropped: ptxas spilled the tile registers inside the loop and the kernel ran 2.8x slower.)
-__device__ __forceinline__ void math_mat_phase(const DecParams& p, const Smem& S, Cons& c, int ph, unsigned& gq, float ss,
-                                               int cw, int lane, unsigned phase_idx, unsigned long long* pm) {
+// consumer state carried from phase to phase: row groups handed over so far and the ring position
+struct MState { unsigned gq, ring; };                          // ring = slot | parity << 8
+__device__ __forceinline__ unsigned long long pack_state(unsigned gq, const Ring& r) {
+    return ((unsigned long long)(r.sl | (r.par << 8)) << 32) | gq;
+}
+__device__ __forceinline__ void unpack_state(unsigned long long st, unsigned& gq, Ring& r) {
+    gq = (unsigned)st;
+    r.sl = (unsigned)(st >> 32) & 0xffu;
+    r.par = (unsigned)(st >> 40) & 1u;
+}
+// this lane's activations of a phase with <= 2 K tiles, from xs into registers (packed for FFMA2; zero past the end)
+__device__ __forceinline__ void load_xr(const Smem& S, const PhaseDesc& d, int cw, int lane, unsigned long long (&xr)[8]) {
+    const int lcol = (cw << 8) + (lane << 3);
+    const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
+#pragma unroll
+    for (int kt = 0; kt < 2; ++kt) {
+        const int c = kt * d.CT + lcol;
+        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+        if (kt < d.KT && lcol < d.CT && c < d.C) {
+            x0 = lds128f(xa + (uint32_t)((kt * d.CT) << 2));
+            x1 = lds128f(xa + (uint32_t)((kt * d.CT) << 2) + 512u);
+        }
+        xr[kt * 4] = pack2(x0.x, x0.y); xr[kt * 4 + 1] = pack2(x0.z, x0.w);
+        xr[kt * 4 + 2] = pack2(x1.x, x1.y); xr[kt * 4 + 3] = pack2(x1.z, x1.w);
+    }
+}
+
+// Stream this CTA's tiles of one matvec phase.  Per tile a warp owns rows 4h..4h+3 of one 256-column chunk (rows past a
+// short group's end hold stale bytes; their sums are never read).  `gq` counts the row groups handed to the epilogue
+// warp since kernel start (hand-off record = gq % kDumpBufs).  XREG: the phase has <= 2 K tiles and this lane's
+// activations (packed for FFMA2; zero for columns past the end) stay in registers; else they are re-read from xs.
+// Out of line on purpose: the function gets its own register allocation (the 16 math warps leave 96 registers per
+// thread), so phase-level state of the caller is parked across the call instead of spilling inside the tile loop.
+template <bool XREG>
+__device__ __noinline__ unsigned long long math_mat_phase(const DecParams& p, int ph, unsigned long long state, float ss, unsigned phase_idx) {
+    const Smem S = smem_view();
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw >> 1, rh = mw & 1;
+    unsigned long long* const pm = (PROF(p) != nullptr && ct == 0) ? PROF(p) + (size_t)blockIdx.x * kProfPhases * 8 : nullptr;
+    Cons c{{0u, 0u}, false};
+    unsigned gq;
+    unpack_state(state, gq, c.ring);
     const PhaseDesc& d = p.ph[ph];
     const int C = d.C, KT = d.KT, CT = d.CT, nsub = d.paired ? 2 : 1;
     const int col = (cw << 8) + (lane << 3);                                  // this lane's first column inside a tile
     const uint32_t xlane_a = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);   // + col0 * 4: first float4; second 512 B on
-    const uint32_t dump_a = S.red_a + (uint32_t)(cw * kRecFloats * 4);            // this warp's record inside a hand-off buffer
+    const uint32_t dump_a = S.red_a + (uint32_t)((cw * 2 + rh) * kRecFloats * 4); // this warp's record inside a hand-off buffer
+    bar_sync(BAR_PAIR0 + cw, 64);                     // the partner's K tiles of this chunk are staged
+    unsigned long long xr[8];
+    if (XREG) load_xr(S, d, cw, lane, xr);
+    mark(pm, p, phase_idx, PROF_PROLOGUE);
     bool first = pm != nullptr;
     int ntile = 0;
+    float pend[kHalf];
+    bool have = false;
     RowIt it;
     it.init(S.misc, ph, d);
     mark(pm, p, phase_idx, PROF_WAIT_FULL);     // schedule computed, about to wait for the first tile
     for (; it.valid(); it.next()) {
         for (int sub = 0; sub < nsub; ++sub) {
-            unsigned long long acc[kRows];                    // (even-column sum, odd-column sum) per row
+            unsigned long long acc[kHalf];                    // (even-column sum, odd-column sum) per row
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) acc[r] = 0ull;
-            int col0 = 0;
-            for (int kt = 0; kt < KT; ++kt, col0 += CT) {
-                TileRegs t;
-                wait_full(p, S, c, 3);
-                if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
-                tile_load(S, c.ring.sl, xlane_a, col, lane, col0, min(CT, C - col0), t);
+            for (int r = 0; r < kHalf; ++r) acc[r] = 0ull;
+            if (XREG) {
 #pragma unroll
-                for (int r = 0; r < kRows; ++r) fma8(t.w[r], t.xp, acc[r]);
-                release_slot(S, c, lane);
-                if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
+                for (int kt = 0; kt < 2; ++kt) {
+                    if (kt < KT) {
+                        const int ncols = min(CT, C - kt * CT);
+                        const uint32_t stride = (uint32_t)ncols * 2u;
+                        const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (uint32_t)(rh * kHalf) * stride + (col < ncols ? (uint32_t)col << 1 : 0u);
+                        wait_full(p, S, c, 3);
+                        if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
+                        uint4 w[kHalf];
+#pragma unroll
+                        for (int r = 0; r < kHalf; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
+                        if (kt == 0 && have) { flush_group(p, S, c, gq, pend, ss, dump_a, lane); have = false; }
+#pragma unroll
+                        for (int r = 0; r < kHalf; ++r) fma8(w[r], &xr[kt * 4], acc[r]);
+                        release_slot(S, c, lane);
+                        if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
+                    }
+                }
+            } else {
+                int col0 = 0;
+                for (int kt = 0; kt < KT; ++kt, col0 += CT) {
+                    const int ncols = min(CT, C - col0);
+                    const bool ok = col < ncols;                       // lanes past a short tile's last column read column 0 against zeros
+                    const uint32_t stride = (uint32_t)ncols * 2u;
+                    const uint32_t xa = ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4);
+                    const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (uint32_t)(rh * kHalf) * stride + (ok ? (uint32_t)col << 1 : 0u);
+                    wait_full(p, S, c, 3);
+                    if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
+                    float4 x0 = lds128f(xa), x1 = lds128f(xa + 512u);
+                    uint4 w[kHalf];
+#pragma unroll
+                    for (int r = 0; r < kHalf; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
+                    if (!ok) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
+                    if (kt == 0 && have) { flush_group(p, S, c, gq, pend, ss, dump_a, lane); have = false; }
+                    const unsigned long long xp[4] = {pack2(x0.x, x0.y), pack2(x0.z, x0.w), pack2(x1.x, x1.y), pack2(x1.z, x1.w)};
+#pragma unroll
+                    for (int r = 0; r < kHalf; ++r) fma8(w[r], xp, acc[r]);
+                    release_slot(S, c, lane);
+                    if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
+                }
             }
-            // Hand the row sums to the epilogue warp.  A transposing shuffle reduction (4 + 2 + 1 exchanges halve the rows
-            // a lane holds while doubling the lanes summed, then 2 plain steps) leaves the warp total of row (lane >> 2) & 7
-            // in every lane; 8 floats per warp go into a ring of kDumpBufs hand-off records, so the math warps can run
-            // kDumpBufs row groups ahead of the epilogue warp (whose per-group latency would otherwise pace the ring drain
-            // at a phase start).  Fixed order of additions: deterministic.
-            float v[kRows];
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) {
+            for (int r = 0; r < kHalf; ++r) {
                 float lo, hi;
                 asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[r]));
-                v[r] = lo + hi;
+                pend[r] = lo + hi;
             }
-            {
-                const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float recv = __shfl_xor_sync(0xffffffffu, u4 ? v[r] : v[r + 4], 16);
-                    v[r] = (u4 ? v[r + 4] : v[r]) + recv;
-                }
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const float recv = __shfl_xor_sync(0xffffffffu, u3 ? v[r] : v[r + 2], 8);
-                    v[r] = (u3 ? v[r + 2] : v[r]) + recv;
-                }
-                const float recv = __shfl_xor_sync(0xffffffffu, u2 ? v[0] : v[1], 4);
-                v[0] = (u2 ? v[1] : v[0]) + recv;
-                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-                v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-            }
-            const unsigned buf = gq & (kDumpBufs - 1), use = gq / kDumpBufs;
-            if (use > 0 && !c.dead) {
-                const uint32_t fb = S.red_free_a + buf * 8;
-                if (!mbar_try_wait(fb, (use - 1) & 1u)) c.dead = !mbar_wait_slow(p, fb, (use - 1) & 1u, 6);
-            }
-            if ((lane & 3) == 0) sts32f(dump_a + (buf * kRedFloats + (unsigned)((lane >> 2) & 7)) * 4u, v[0]);
-            if (lane == 1) sts32f(dump_a + (buf * kRedFloats + kRows) * 4u, ss);      // this warp's share of sum(v^2) (norm phases)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(S.red_full_a + buf * 8);
-            ++gq;
+            have = true;
         }
     }
+    if (have) flush_group(p, S, c, gq, pend, ss, dump_a, lane);
     mark(pm, p, phase_idx, PROF_LAST_TILE);
+    bar_sync(BAR_PAIR0 + cw, 64);                 // both warps are done reading xs before the next prologue overwrites it
+    return pack_state(gq, c.ring);
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -657,7 +721,7 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 // all loads in flight together, repeated until every element carries `epoch` -- that IS the synchronisation with the
 // CTAs that produce the vector (no grid barrier on these transitions).  After a stale read the lane first spins on the one
 // stale element (8 bytes per round instead of 64 * NCH), then reads everything again.  Bounded by the watchdog.
-template <int NCH, bool SYS = false>
+template <int NCH>
 __device__ __forceinline__ void load_flagged(const DecParams& p, const unsigned long long* vec, const int (&col)[NCH], unsigned epoch,
                                              unsigned long long (&e)[NCH * 8], bool& dead) {
     unsigned long long t0 = 0;
@@ -667,10 +731,7 @@ __device__ __forceinline__ void load_flagged(const DecParams& p, const unsigned 
         for (int u = 0; u < NCH; ++u) {
             if (col[u] >= 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (SYS) ld_flagged2_sys(vec + col[u] + 2 * j, e[u * 8 + 2 * j], e[u * 8 + 2 * j + 1]);
-                    else ld_flagged2(vec + col[u] + 2 * j, e[u * 8 + 2 * j], e[u * 8 + 2 * j + 1]);
-                }
+                for (int j = 0; j < 4; ++j) ld_flagged2(vec + col[u] + 2 * j, e[u * 8 + 2 * j], e[u * 8 + 2 * j + 1]);
             }
         }
         int stale = -1;
@@ -685,37 +746,48 @@ __device__ __forceinline__ void load_flagged(const DecParams& p, const unsigned 
         if (p.poll_single) {
             unsigned long long w;
             do {
-                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(vec + stale) : "memory");
-                if ((++it & 63u) == 0u) {
-                    if (t0 == 0) t0 = gtimer();
-                    if (aborted(p)) { dead = true; break; }
-                    if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x500u, (unsigned)stale, epoch); dead = true; break; }
-                }
+                w = ld_flagged1(vec + stale);
+                if ((++it & 63u) == 0u && poll_watchdog(p.status, p.timeout_ns, t0, 0x500u, (unsigned)stale, epoch)) { dead = true; break; }
             } while ((unsigned)(w >> 32) != epoch);
-        } else if ((++it & 63u) == 0u) {
-            if (t0 == 0) t0 = gtimer();
-            if (aborted(p)) dead = true;
-            else if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x500u, (unsigned)stale, epoch); dead = true; }
+        } else if ((++it & 63u) == 0u && poll_watchdog(p.status, p.timeout_ns, t0, 0x500u, (unsigned)stale, epoch)) {
+            dead = true;
         }
     }
 }
 __device__ __forceinline__ float4 flagged_f4(const unsigned long long* e) {
     return make_float4(__uint_as_float((unsigned)e[0]), __uint_as_float((unsigned)e[1]), __uint_as_float((unsigned)e[2]), __uint_as_float((unsigned)e[3]));
 }
+// one flagged element, polled until it carries `epoch`
+__device__ __forceinline__ float wait_flagged1(const DecParams& p, const unsigned long long* ptr, unsigned epoch, bool& dead) {
+    unsigned long long t0 = 0, w;
+    unsigned it = 0;
+    while (true) {
+        w = ld_flagged1(ptr);
+        if ((unsigned)(w >> 32) == epoch || dead || p.nosync) break;
+        if ((++it & 63u) == 0u && poll_watchdog(p.status, p.timeout_ns, t0, 0x501u, 0u, epoch)) { dead = true; break; }
+    }
+    return __uint_as_float((unsigned)w);
+}
 
 // Single-query attention over this CTA's (head, KV split) units (cmdbuf_mat_mul QK^T * 1/sqrt(D),
 // cmdbuf_row_softmax, cmdbuf_mat_mul P*V; th-llama.cpp:365-380).  Every warp runs its own online
-// softmax over the positions j = warp (mod 8) of each K/V tile pair -- no CTA barrier per tile -- and
-// the 8 warps are merged once per unit.  The split results {m, l, o[D]} go to p.part; the Wo
+// softmax over the positions j = warp (mod 16) of each K/V tile pair -- no CTA barrier per tile -- and
+// the 16 warps are merged once per unit.  The split results {m, l, o[D]} go to p.part; the Wo
 // prologue merges the splits of a head.
-__device__ __forceinline__ void math_att_phase(const DecParams& p, const Smem& S, Cons& c, const thk_llama_layer& L, int ct, int cw, int lane) {
+__device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, unsigned long long state, int layer) {
+    const Smem S = smem_view();
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31;
+    Cons c{{0u, 0u}, false};
+    unsigned gq;
+    unpack_state(state, gq, c.ring);
+    const thk_llama_layer L = p.layers[layer];
     const AttSched a = make_att(p);
     const int D = p.head_dim;
     const float scale = 1.0f / sqrtf((float)D);
     const bool act = lane < (D >> 2);
-    float* sc_o = S.red + kAttScratchOff;             // [8][128]
-    float* sc_m = sc_o + kMathWarps * kMaxHeadDim;    // [8]
-    float* sc_l = sc_m + kMathWarps;                  // [8]
+    float* sc_o = S.red + kAttScratchOff;             // [16][128]
+    float* sc_m = sc_o + kMathWarps * kMaxHeadDim;    // [16]
+    float* sc_l = sc_m + kMathWarps;                  // [16]
     float* sc_kn = sc_l + kMathWarps;                 // [128] the new position's K row (warp 0 only)
     float* sc_vn = sc_kn + kMaxHeadDim;               // [128] ... and V row
     for (int u = blockIdx.x; u < p.Hl * a.S; u += gridDim.x) {
@@ -727,7 +799,7 @@ __device__ __forceinline__ void math_att_phase(const DecParams& p, const Smem& S
         float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
             q4 = __ldcg((const float4*)(p.q + h * D) + lane);
-            if (has_new && cw == 0) {   // the token's own K/V row (QKV epilogue of this launch): same L2 round trip as q,
+            if (has_new && mw == 0) {   // the token's own K/V row (QKV epilogue of this launch): same L2 round trip as q,
                 const size_t off = ((size_t)h * p.n_ctx + p.n_past) * D;     // parked in shared memory until the tiles are done
                 const float4 kn4 = __ldcg((const float4*)(L.key_cache + off) + lane);
                 const float4 vn4 = __ldcg((const float4*)(L.value_cache + off) + lane);
@@ -747,7 +819,7 @@ __device__ __forceinline__ void math_att_phase(const DecParams& p, const Smem& S
             wait_full(p, S, cv, 5);
             const float* vt = (const float*)(S.slots + cv.ring.sl * kSlotBytes);
             c.dead = c.dead || cv.dead;
-            for (int j0 = cw; j0 < np; j0 += 4 * kMathWarps) {      // 4 positions of this warp per round
+            for (int j0 = mw; j0 < np; j0 += 4 * kMathWarps) {      // 4 positions of this warp per round
                 float s[4];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -783,7 +855,7 @@ __device__ __forceinline__ void math_att_phase(const DecParams& p, const Smem& S
             release_slot(S, c, lane);
             release_slot(S, c, lane);
         }
-        if (has_new && cw == 0) {   // the token's own position
+        if (has_new && mw == 0) {   // the token's own position
             float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
             float sdot = 0.f;
             if (act) {
@@ -799,9 +871,9 @@ __device__ __forceinline__ void math_att_phase(const DecParams& p, const Smem& S
             o4.x = fmaf(pj, v4.x, o4.x * corr); o4.y = fmaf(pj, v4.y, o4.y * corr);
             o4.z = fmaf(pj, v4.z, o4.z * corr); o4.w = fmaf(pj, v4.w, o4.w * corr);
         }
-        // merge the 8 warps (fixed order -> deterministic)
-        if (act) *(float4*)(sc_o + cw * kMaxHeadDim + (lane << 2)) = o4;
-        if (lane == 0) { sc_m[cw] = m; sc_l[cw] = lsum; }
+        // merge the 16 warps (fixed order -> deterministic)
+        if (act) *(float4*)(sc_o + mw * kMaxHeadDim + (lane << 2)) = o4;
+        if (lane == 0) { sc_m[mw] = m; sc_l[mw] = lsum; }
         bar_sync(BAR_MATH, kMathThreads);
         if (ct < D) {
             float M = sc_m[0];
@@ -820,54 +892,43 @@ __device__ __forceinline__ void math_att_phase(const DecParams& p, const Smem& S
         }
         bar_sync(BAR_MATH, kMathThreads);   // scratch reuse by the next unit
     }
+    return pack_state(gq, c.ring);
 }
 
 // ---- prologues: stage the phase's activation vector in shared memory (permuted layout) ----
+// Chunk c of every K tile is multiplied by the two warps (c, 0) and (c, 1) only, and within a chunk a lane only ever
+// touches its own 8 columns.  Warp (c, h) stages the K tiles kt = h, h + 2, ... of chunk c; a 64-thread named barrier
+// (BAR_PAIR0 + c) publishes them to its partner.  No CTA-wide barrier, no cross-chunk traffic.
 __device__ __forceinline__ float4 emb_f4(const uint16_t* row, int i) {
     const uint2 u = __ldg((const uint2*)(row + i));
     const float2 a = h2_to_f2(u.x), b = h2_to_f2(u.y);
     return make_float4(a.x, a.y, b.x, b.y);
 }
-// v = src (+ the tp partial vectors of exchange `which`, in rank order); src == nullptr: the embedding row
-__device__ __forceinline__ float4 load_summed(const DecParams& p, const float* src, const uint16_t* emb_row, int which, int i) {
-    float4 v = src ? __ldcg((const float4*)(src + i)) : emb_f4(emb_row, i);
-    if (which >= 0) {
-        for (int r = 0; r < p.tp_size; ++r) {
-            const float4 a = __ldcg((const float4*)(xb_ptr(p, p.tp_rank, which, r) + i));
-            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-        }
-    }
-    return v;
-}
-// ---- prologues ----
-// A math warp only ever multiplies against ITS columns of the activation vector: chunk kt * CT/256 + cw of every K tile,
-// and within a chunk a lane only its own 8 columns.  So the staged vector xs is lane-private storage: every lane loads,
-// transforms and stores exactly the values it will read back in the tile loop -- no CTA barrier, no cross-warp traffic,
-// and a warp starts on its first tile as soon as its own loads have landed.
-__device__ __forceinline__ void sts128f(uint32_t a, const float4& v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 
-// xs <- v * gain, v = the residual stream (cmdbuf_rms_norm + cmdbuf_row_element_multiply, th.cpp:1153-1200,1298-1315; under
-// tensor parallelism the residual adds of th-llama.cpp:409/447 move here).  The RMS scale 1/sqrt(mean(v^2) + 1e-6) is a
-// scalar, so it is applied to the finished row sums by the epilogue warp instead: here every warp only leaves its share
-// of sum(v^2) (returned; it travels to the epilogue warp inside every hand-off record).  When `out` is given, v is also written back as the new residual stream, each float4
-// by exactly one CTA.  `fsrc` != nullptr: v comes from a flagged vector (waits for `epoch`), else from src / the embedding
-// row (after a grid barrier).  The gain was L2-prefetched during the previous phase.
-__device__ __forceinline__ float prologue_norm(const DecParams& p, const Smem& S, const PhaseDesc& d, const float* src, const uint16_t* emb_row,
-                                               const unsigned long long* fsrc, unsigned epoch, const float* gain, int which, float* out,
-                                               int cw, int lane, bool& dead) {
+// xs <- v * gain, v = the residual stream (cmdbuf_rms_norm + cmdbuf_row_element_multiply, th.cpp:1153-1200,1298-1315).
+// The RMS scale 1/sqrt(mean(v^2) + 1e-6) is a scalar, so it is applied to the finished row sums by the epilogue warp
+// instead: here every warp only leaves its share of sum(v^2) (returned; it travels to the epilogue warp inside every
+// hand-off record).  fsrc != nullptr: v comes from a flagged vector (waits for `epoch`); else v is the embedding row
+// (first phase of a launch), which is also published as the flagged residual stream `xf_out` (epoch `epoch`), every
+// element by exactly one CTA.  The gain was L2-prefetched during the previous phase.
+__device__ __noinline__ float prologue_norm(const DecParams& p, int ph, const uint16_t* emb_row, const unsigned long long* fsrc, unsigned epoch,
+                                            const float* gain, unsigned long long* xf_out) {
+    const Smem S = smem_view();
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw >> 1, rh = mw & 1;
+    const PhaseDesc& d = p.ph[ph];
+    bool dead = false;
     const int n = d.C;
     const int lcol = (cw << 8) + (lane << 3);                 // this lane's first column inside a K tile
     const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
     float ss = 0.f;
-    for (int kt0 = 0; kt0 < d.KT; kt0 += 2) {                 // two K tiles per L2 round trip
+    for (int kt0 = rh; kt0 < d.KT; kt0 += 4) {                // this warp's K tiles kt0 and kt0 + 2 per L2 round trip
         float4 v[4], g[4];
         int col[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const int c = (kt0 + u) * d.CT + lcol;
-            col[u] = (kt0 + u < d.KT && lcol < d.CT && c < n) ? c : -1;
+            const int kt = kt0 + 2 * u;
+            const int c = kt * d.CT + lcol;
+            col[u] = (kt < d.KT && lcol < d.CT && c < n) ? c : -1;
             if (col[u] >= 0) {
                 g[2 * u] = __ldg((const float4*)(gain + c));
                 g[2 * u + 1] = __ldg((const float4*)(gain + c + 4));
@@ -880,10 +941,7 @@ __device__ __forceinline__ float prologue_norm(const DecParams& p, const Smem& S
             for (int u = 0; u < 2; ++u) if (col[u] >= 0) { v[2 * u] = flagged_f4(e + 8 * u); v[2 * u + 1] = flagged_f4(e + 8 * u + 4); }
         } else {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) if (col[u] >= 0) {
-                v[2 * u] = load_summed(p, src, emb_row, which, col[u]);
-                v[2 * u + 1] = load_summed(p, src, emb_row, which, col[u] + 4);
-            }
+            for (int u = 0; u < 2; ++u) if (col[u] >= 0) { v[2 * u] = emb_f4(emb_row, col[u]); v[2 * u + 1] = emb_f4(emb_row, col[u] + 4); }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -893,97 +951,41 @@ __device__ __forceinline__ float prologue_norm(const DecParams& p, const Smem& S
                     const float4 t = v[2 * u + hh], gg = g[2 * u + hh];
                     ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
                     const int i = col[u] + 4 * hh;
-                    if (out && (unsigned)(i >> 2) % gridDim.x == blockIdx.x) *(float4*)(out + i) = t;
-                    sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2) + 512u * hh, make_float4(t.x * gg.x, t.y * gg.y, t.z * gg.z, t.w * gg.w));
+                    if (xf_out && (unsigned)(i >> 2) % gridDim.x == blockIdx.x) {
+                        st_flagged(xf_out + i, t.x, epoch); st_flagged(xf_out + i + 1, t.y, epoch);
+                        st_flagged(xf_out + i + 2, t.z, epoch); st_flagged(xf_out + i + 3, t.w, epoch);
+                    }
+                    sts128f(xa + (uint32_t)(((kt0 + 2 * u) * d.CT) << 2) + 512u * hh, make_float4(t.x * gg.x, t.y * gg.y, t.z * gg.z, t.w * gg.w));
                 }
             }
         }
     }
     return warp_sum(ss);
 }
-// Tensor-parallel variant (dataflow): the residual stream lives lane-privately in shared memory (every CTA of every rank
-// holds the whole vector, each lane the columns it multiplies against), so the all-reduce is finished right here:
-// v = residual + the tp flagged partial vectors that the Wo / W2 epilogues of ALL ranks pushed into this rank's exchange
-// region over NVLink (rank order: bitwise identical on every rank); reading them IS the cross-GPU synchronisation.
-// which < 0: v is the embedding row (first phase of a launch).
-// Every CTA reads all tp partial vectors (tp x 32 KB): fine at tp 2 and 4 (568 / 599 tok/s), too much L2 polling traffic
-// at tp 8 (432 tok/s).  A two-hop version (each CTA reduces 1/gridDim of the vector, then everyone reads the sums) is the
-// next step; a first attempt faulted on the GPU and was backed out.
-__device__ __forceinline__ float prologue_norm_tp(const DecParams& p, const Smem& S, const PhaseDesc& d, const uint16_t* emb_row, int which, unsigned epoch,
-                                                  const float* gain, float* out, int cw, int lane, bool& dead) {
+// xs <- the FFN hidden vector for W2, from the flagged vector (waits for `epoch`)
+__device__ __noinline__ void prologue_copy(const DecParams& p, int ph, const unsigned long long* fsrc, unsigned epoch) {
+    const Smem S = smem_view();
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw >> 1, rh = mw & 1;
+    const PhaseDesc& d = p.ph[ph];
+    bool dead = false;
     const int n = d.C;
     const int lcol = (cw << 8) + (lane << 3);
     const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
-    const uint32_t ra = xa + p.res_off;
-    const unsigned long long* xbf = (const unsigned long long*)p.xchg[p.tp_rank];
-    float ss = 0.f;
-    for (int kt = 0; kt < d.KT; ++kt) {
-        const int c = kt * d.CT + lcol;
-        if (lcol >= d.CT || c >= n) continue;
-        const uint32_t off = (uint32_t)((kt * d.CT) << 2);
-        const float4 g0 = __ldg((const float4*)(gain + c)), g1 = __ldg((const float4*)(gain + c + 4));
-        float4 v0, v1;
-        if (which < 0) {
-            v0 = emb_f4(emb_row, c);
-            v1 = emb_f4(emb_row, c + 4);
-        } else {
-            v0 = lds128f(ra + off);
-            v1 = lds128f(ra + off + 512u);
-            for (int r0 = 0; r0 < p.tp_size; r0 += 4) {
-                int col[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) col[u] = (r0 + u < p.tp_size) ? (int)(((size_t)which * p.tp_size + r0 + u) * p.n_embd) + c : -1;
-                unsigned long long e[32];
-                load_flagged<4, true>(p, xbf, col, epoch, e, dead);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) if (col[u] >= 0) {
-                    const float4 a = flagged_f4(e + 8 * u), b = flagged_f4(e + 8 * u + 4);
-                    v0.x += a.x; v0.y += a.y; v0.z += a.z; v0.w += a.w;
-                    v1.x += b.x; v1.y += b.y; v1.z += b.z; v1.w += b.w;
-                }
-            }
-        }
-        sts128f(ra + off, v0);
-        sts128f(ra + off + 512u, v1);
-        ss = fmaf(v0.x, v0.x, ss); ss = fmaf(v0.y, v0.y, ss); ss = fmaf(v0.z, v0.z, ss); ss = fmaf(v0.w, v0.w, ss);
-        ss = fmaf(v1.x, v1.x, ss); ss = fmaf(v1.y, v1.y, ss); ss = fmaf(v1.z, v1.z, ss); ss = fmaf(v1.w, v1.w, ss);
-        if (out && (unsigned)(c >> 3) % gridDim.x == blockIdx.x) { *(float4*)(out + c) = v0; *(float4*)(out + c + 4) = v1; }
-        sts128f(xa + off, make_float4(v0.x * g0.x, v0.y * g0.y, v0.z * g0.z, v0.w * g0.w));
-        sts128f(xa + off + 512u, make_float4(v1.x * g1.x, v1.y * g1.y, v1.z * g1.z, v1.w * g1.w));
-    }
-    return warp_sum(ss);
-}
-// xs <- src (the FFN hidden vector for W2); fsrc != nullptr: from the flagged vector, waiting for `epoch`
-__device__ __forceinline__ void prologue_copy(const DecParams& p, const Smem& S, const PhaseDesc& d, const float* src, const unsigned long long* fsrc,
-                                              unsigned epoch, int cw, int lane, bool& dead) {
-    const int n = d.C;
-    const int lcol = (cw << 8) + (lane << 3);
-    const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
-    for (int kt0 = 0; kt0 < d.KT; kt0 += 3) {                 // three K tiles per L2 round trip
-        float4 v[6];
+    for (int kt0 = rh; kt0 < d.KT; kt0 += 6) {                // this warp's K tiles kt0, kt0 + 2, kt0 + 4 per L2 round trip
         int col[3];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-            const int c = (kt0 + u) * d.CT + lcol;
-            col[u] = (kt0 + u < d.KT && lcol < d.CT && c < n) ? c : -1;
+            const int kt = kt0 + 2 * u;
+            const int c = kt * d.CT + lcol;
+            col[u] = (kt < d.KT && lcol < d.CT && c < n) ? c : -1;
         }
-        if (fsrc != nullptr) {
-            unsigned long long e[24];
-            load_flagged<3>(p, fsrc, col, epoch, e, dead);
-#pragma unroll
-            for (int u = 0; u < 3; ++u) if (col[u] >= 0) { v[2 * u] = flagged_f4(e + 8 * u); v[2 * u + 1] = flagged_f4(e + 8 * u + 4); }
-        } else {
-#pragma unroll
-            for (int u = 0; u < 3; ++u) if (col[u] >= 0) {
-                v[2 * u] = __ldcg((const float4*)(src + col[u]));
-                v[2 * u + 1] = __ldcg((const float4*)(src + col[u] + 4));
-            }
-        }
+        unsigned long long e[24];
+        load_flagged<3>(p, fsrc, col, epoch, e, dead);
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             if (col[u] >= 0) {
-                sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2), v[2 * u]);
-                sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2) + 512u, v[2 * u + 1]);
+                sts128f(xa + (uint32_t)(((kt0 + 2 * u) * d.CT) << 2), flagged_f4(e + 8 * u));
+                sts128f(xa + (uint32_t)(((kt0 + 2 * u) * d.CT) << 2) + 512u, flagged_f4(e + 8 * u + 4));
             }
         }
     }
@@ -993,55 +995,15 @@ __device__ __forceinline__ void prologue_copy(const DecParams& p, const Smem& S,
 // in flight together (~0.6 us per L2 round trip under the weight stream).  (A flagged, barrier-free version of the
 // QKV -> attention -> Wo hand-overs was built and measured slower: 2.69 -> 2.96 ms/token -- the polling of 128 split
 // records by every CTA costs more than the two grid barriers it removes.)
-#ifdef THK_MERGE1
-__device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Smem& S, const PhaseDesc& d, int cw, int lane) {
+__device__ __noinline__ void prologue_att_merge(const DecParams& p, int ph) {
+    const Smem S = smem_view();
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw >> 1, rh = mw & 1;
+    const PhaseDesc& d = p.ph[ph];
     const AttSched a = make_att(p);
     const int D = p.head_dim, ps = part_stride(p);
     const int lcol = (cw << 8) + (lane << 3);
     const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
-    for (int q = 0; q < 2 * d.KT; ++q) {                      // (K tile, half) -> one float4 of this lane's columns
-        const int kt = q >> 1, hh = q & 1;
-        const int c = kt * d.CT + lcol;
-        if (lcol >= d.CT || c >= d.C) continue;
-        const int i = c + 4 * hh;
-        const int h = i / D, dd = i - h * D;
-        const float* ph = p.part + (size_t)h * a.S * ps;
-        float M = -INFINITY, lt = 0.f;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < a.S; s0 += 4) {
-            float2 ml[4];
-            float4 v[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) if (s0 + t < a.S) {
-                const float* r = ph + (s0 + t) * ps;
-                ml[t] = __ldcg((const float2*)r);
-                v[t] = __ldcg((const float4*)(r + 4 + dd));
-            }
-            float Mn = M;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) if (s0 + t < a.S) Mn = fmaxf(Mn, ml[t].x);
-            const float c0 = expf(M - Mn);                   // first round: exp(-inf) = 0
-            lt *= c0;
-            o.x *= c0; o.y *= c0; o.z *= c0; o.w *= c0;
-            M = Mn;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) if (s0 + t < a.S) {
-                const float e = expf(ml[t].x - M);
-                lt = fmaf(ml[t].y, e, lt);
-                o.x = fmaf(v[t].x, e, o.x); o.y = fmaf(v[t].y, e, o.y); o.z = fmaf(v[t].z, e, o.z); o.w = fmaf(v[t].w, e, o.w);
-            }
-        }
-        o.x /= lt; o.y /= lt; o.z /= lt; o.w /= lt;
-        sts128f(xa + (uint32_t)((kt * d.CT) << 2) + 512u * hh, o);
-    }
-}
-#else
-__device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Smem& S, const PhaseDesc& d, int cw, int lane) {
-    const AttSched a = make_att(p);
-    const int D = p.head_dim, ps = part_stride(p);
-    const int lcol = (cw << 8) + (lane << 3);
-    const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
-    for (int kt = 0; kt < d.KT; ++kt) {
+    for (int kt = rh; kt < d.KT; kt += 2) {
         const int c = kt * d.CT + lcol;
         if (lcol >= d.CT || c >= d.C) continue;
         const int h = c / D, dd = c - h * D;                  // 8 consecutive columns never straddle a head (D % 8 == 0)
@@ -1080,26 +1042,18 @@ __device__ __forceinline__ void prologue_att_merge(const DecParams& p, const Sme
         sts128f(xa + (uint32_t)((kt * d.CT) << 2) + 512u, o1);
     }
 }
-#endif
-
 __device__ __forceinline__ void prefetch_gain(const float* gain, int n, int ct) {
     for (int off = ct * 32; off < n; off += kMathThreads * 32)       // one 128-byte line per thread
         asm volatile("prefetch.global.L2 [%0];" ::"l"(gain + off));
 }
 
-template <bool kTP>
-__device__ void math_main(const DecParams& p, const Smem& S) {
-    const int ct = (int)threadIdx.x - kMathBase, cw = ct >> 5, lane = ct & 31;
+__device__ void math_main(const DecParams& p, int tok) {
+    const int ct = (int)threadIdx.x - kMathBase;
     unsigned long long* const pm = (PROF(p) != nullptr && ct == 0) ? PROF(p) + (size_t)blockIdx.x * kProfPhases * 8 : nullptr;
-    Cons c{{0u, 0u}, false};
-    unsigned gq = 0;
-    int tok = *p.token;
-    if (tok < 0 || tok >= p.n_vocab) { if (ct == 0) raise_abort(p, 0x300u, (unsigned)tok, 0); tok = 0; }
+    unsigned long long state = 0ull;      // row groups handed over, ring position
     const uint16_t* emb_row = p.emb + (size_t)tok * p.n_embd;
-    if (blockIdx.x == 0 && ct == 0) *p.bar_next = 0u;   // arm the next launch's barrier counter
     mark(pm, p, 0, PROF_START);
     const int nsteps = 5 * p.n_layer + 1;
-    constexpr bool tp = kTP;             // compile-time: the single-GPU kernel carries no tensor-parallel code
     int l = 0, k = K_QKV;
     float ss = 0.f;                       // this warp's share of sum(v^2) of the current norm phase's input
     for (int i = 0; i < nsteps; ++i) {
@@ -1108,32 +1062,30 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
         const unsigned epoch = p.flag_epoch + (unsigned)l + 1u;          // flagged vectors written in layer l (K_QKV / K_OUT read layer l-1's x)
         if (k == K_QKV || k == K_W13 || k == K_OUT) {
             const float* gain = (k == K_QKV) ? L->attention_norm : (k == K_W13) ? L->ffn_norm : p.norm;
-            // step 0: x <- f32(tok_embeddings[token]) (th-llama.cpp:577-585; device-side like :552-575): every CTA
-            // converts the row itself and one copy goes to p.x for the Wo residual.  Under tensor parallelism the
-            // W13 / QKV prologues also finish the all-reduce: h1 = x + sum of Wo partials, x = h1 + sum of W2 partials.
-            const float* src = i == 0 ? nullptr : (k == K_W13) ? (tp ? p.x : p.h1) : (tp ? p.h1 : p.x);
-            const unsigned long long* fsrc = (i == 0 || !p.dataflow || tp) ? nullptr : (k == K_W13 ? p.h1f : p.xf);
-            const int which = (i == 0 || !tp) ? -1 : (k == K_W13 ? 0 : 1);
-            float* out = i == 0 ? p.x : !tp ? nullptr : (k == K_W13 ? p.h1 : p.x);
-            if (tp && p.dataflow)
-                ss = prologue_norm_tp(p, S, p.ph[phase_of(k)], emb_row, which, k == K_W13 ? epoch : epoch - 1u, gain, (i == 0 || k == K_OUT) ? p.x : nullptr, cw, lane, c.dead);
-            else
-                ss = prologue_norm(p, S, p.ph[phase_of(k)], src, emb_row, fsrc, k == K_W13 ? epoch : epoch - 1u, gain, which, out, cw, lane, c.dead);
+            // step 0: x <- f32(tok_embeddings[token]) (th-llama.cpp:577-585; device-side like :552-575): every CTA converts
+            // the row itself and publishes its share as the flagged residual stream (the Wo epilogue / the reducer adds to it)
+            const unsigned long long* fsrc = i == 0 ? nullptr : (k == K_W13 ? p.h1f : p.xf);
+            ss = prologue_norm(p, phase_of(k), emb_row, fsrc, k == K_W13 ? epoch : epoch - 1u, gain, i == 0 ? p.xf : nullptr);
         } else if (k == K_WO) {
-            prologue_att_merge(p, S, p.ph[PH_WO], cw, lane);
+            prologue_att_merge(p, PH_WO);
         } else if (k == K_W2) {
-            prologue_copy(p, S, p.ph[PH_W2], p.ff, p.dataflow ? p.fff : nullptr, epoch, cw, lane, c.dead);
+            prologue_copy(p, PH_W2, p.fff, epoch);
         }
-        mark(pm, p, (unsigned)i, PROF_PROLOGUE);
         // ---- tiles ----
-        if (k == K_ATT) math_att_phase(p, S, c, *L, ct, cw, lane);
-        else math_mat_phase(p, S, c, phase_of(k), gq, ss, cw, lane, (unsigned)i, pm);
+        if (k == K_ATT) {
+            mark(pm, p, (unsigned)i, PROF_PROLOGUE);
+            state = math_att_phase(p, state, l);
+        } else if (p.ph[phase_of(k)].KT <= 2) {
+            state = math_mat_phase<true>(p, phase_of(k), state, ss, (unsigned)i);
+        } else {
+            state = math_mat_phase<false>(p, phase_of(k), state, ss, (unsigned)i);
+        }
         if (k == K_OUT) break;
         // ---- next phase's gain while the grid barrier forms ----
         if (k == K_WO) prefetch_gain(L->ffn_norm, p.n_embd, ct);
         else if (k == K_W2) prefetch_gain(l + 1 < p.n_layer ? p.layers[l + 1].attention_norm : p.norm, p.n_embd, ct);
         mark(pm, p, (unsigned)i, PROF_ARRIVE);
-        if (!(p.dataflow && (k == K_WO || k == K_W13 || k == K_W2))) {   // else: the next prologue waits on the flagged vector itself
+        if (k == K_QKV || k == K_ATT) {                  // (Wo -> W13 -> W2 -> QKV: the next prologue waits on the flagged vector itself)
             if (k == K_ATT) bar_sync(BAR_PRE, kMathThreads + 32);    // our global writes (split results) precede the epilogue warp's arrive
             bar_sync(BAR_ALL, kMathThreads + 32);                     // the epilogue warp has passed the grid barrier
         }
@@ -1149,9 +1101,7 @@ __device__ void math_main(const DecParams& p, const Smem& S) {
 // (and, in the attention phase, the math warps that met it at BAR_PRE) wrote global data in the phase;
 // __syncwarp / bar.sync order those writes before lane 0's gpu-scope release (cumulativity), and the
 // acquire fence + BAR_ALL make the other CTAs' writes visible to every thread here (read with .cg).
-template <bool kTP>
-__device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, int lane, bool& dead, int xset = -1, unsigned epoch = 0u) {
-    if (kTP && xset >= 0) __threadfence_system();      // this warp's pushes to the peers are visible system-wide
+__device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, int lane, bool& dead) {
     __syncwarp();
     if (lane == 0 && !dead && !p.nosync) {
         unsigned* const ctr = p.bar_ctr;
@@ -1160,32 +1110,9 @@ __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, 
         unsigned long long t0 = 0;
         unsigned it = 0;
         while (ld_relaxed_u32(ctr) < target) {    // (pipelined polling, 4 loads in flight, was measured slower: 2.80 -> 2.87 ms/token)
-            if ((++it & 63u) == 0u) {
-                if (t0 == 0) t0 = gtimer();
-                if (aborted(p)) { dead = true; break; }
-                if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x200u, nbar, target); dead = true; break; }
-            }
+            if ((++it & 63u) == 0u && poll_watchdog(p.status, p.timeout_ns, t0, 0x200u, nbar, target)) { dead = true; break; }
         }
         asm volatile("fence.acquire.gpu;" ::: "memory");
-        if (kTP && xset >= 0 && !dead) {
-            // Cross-GPU step of the one-shot all-reduce: every local CTA has pushed its partial rows into all
-            // peers (system-scope fenced before arriving here); rank-level flag tells the peers "my part is in".
-            if (blockIdx.x == 0) {
-                __threadfence_system();
-                for (int d = 0; d < p.tp_size; ++d) st_release_sys(xflags(p, d, xset) + p.tp_rank, epoch);
-            }
-            t0 = 0; it = 0;
-            for (int src = 0; src < p.tp_size && !dead; ++src) {
-                const unsigned* f = xflags(p, p.tp_rank, xset) + src;
-                while ((int)(ld_acquire_sys(f) - epoch) < 0) {
-                    if ((++it & 63u) == 0u) {
-                        if (t0 == 0) t0 = gtimer();
-                        if (aborted(p)) { dead = true; break; }
-                        if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x400u, (unsigned)src, epoch); dead = true; break; }
-                    }
-                }
-            }
-        }
     }
     dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
 }
@@ -1199,41 +1126,50 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
     const PhaseDesc& d = p.ph[ph];
     const int D = p.head_dim, tp_size = kTP ? p.tp_size : 1, tp_rank = kTP ? p.tp_rank : 0, n_ctx = p.n_ctx, n_past = p.n_past;
     const int nsub = d.paired ? 2 : 1;
-    const int rr = lane & 7, qq = lane >> 3;          // this lane adds row rr of math warps 2 qq and 2 qq + 1
-    const uint32_t my_a = S.red_a + (uint32_t)((2 * qq * kRecFloats + rr) * 4);
+    // lane (r, q): row r = lane & 7 of the group (row half r >> 2), chunks 2q and 2q + 1
+    const int rr = lane & 7, qq = lane >> 3;
+    const uint32_t my_a = S.red_a + (uint32_t)((((4 * qq) + (rr >> 2)) * kRecFloats + (rr & 3)) * 4);
     const bool has_resid = (kind == EPI_WO || kind == EPI_W2) && !kTP;
     const bool need_scale = (kind == EPI_QKV || kind == EPI_W13 || kind == EPI_OUT);
     bool have_scale = false;
     float scale = 1.0f;
-    const float* resid_src = (kind == EPI_WO) ? p.x : p.h1;
+    // The residual operand comes from the flagged vector the phase input was derived from (x entering the layer for Wo,
+    // h1 for W2): 32 rows per poll, one per lane, refilled every fourth row group -- its L2 round trip is off the
+    // per-group path, and the epoch check makes the read self-synchronising.
+    const unsigned long long* rsrc = (kind == EPI_WO) ? p.xf : p.h1f;
+    const unsigned repoch = (kind == EPI_WO) ? epoch - 1u : epoch;
+    int rbase = -(1 << 30);
+    float rval = 0.f;
     RowIt it;
     it.init(S.misc, ph, d);
-    // the residual operand of a row group is requested one group ahead: its L2 round trip (~0.6 us under the weight
-    // stream) would otherwise sit on this warp's serial per-group path
-    float resid_next = 0.f;
-    if (has_resid && it.valid() && lane < it.nrows) resid_next = __ldcg(resid_src + it.row0 + lane);
     while (it.valid()) {
         const int row0 = it.row0, nrows = it.nrows, si_cur = it.si;
-        it.next();                                   // `it` now describes the NEXT group
+        it.next();
         for (int sub = 0; sub < nsub; ++sub) {
             const int si = d.paired ? sub : si_cur;
-            const float resid = resid_next;
-            if (has_resid && it.valid() && lane < it.nrows) resid_next = __ldcg(resid_src + it.row0 + lane);
+            float resid = 0.f;
+            if (has_resid) {
+                if (row0 + nrows > rbase + 32) {
+                    rbase = row0;
+                    rval = wait_flagged1(p, rsrc + min(rbase + lane, p.n_embd - 1), repoch, dead);
+                }
+                resid = __shfl_sync(0xffffffffu, rval, (row0 - rbase + rr) & 31);
+            }
             const unsigned buf = gq & (kDumpBufs - 1), use = gq / kDumpBufs;
             if (!dead) {
                 const uint32_t fb = S.red_full_a + buf * 8;
-                if (!mbar_try_wait(fb, use & 1u)) dead = !mbar_wait_slow(p, fb, use & 1u, 7);
+                if (!mbar_try_wait(fb, use & 1u)) dead = !mbar_wait_slow(p.status, p.timeout_ns, fb, use & 1u, 7);
             }
             const uint32_t src = my_a + buf * (uint32_t)(kRedFloats * 4);
-            float y = lds32f(src) + lds32f(src + kRecFloats * 4);
+            float y = lds32f(src) + lds32f(src + 2 * kRecFloats * 4);
             y += __shfl_xor_sync(0xffffffffu, y, 8);
             y += __shfl_xor_sync(0xffffffffu, y, 16);      // every lane: total of row (lane & 7)
             if (need_scale && !have_scale) {
-                // RMSNorm scale of this phase's input (th.cpp:1153-1200): every hand-off record carries the eight warps' shares
-                // of sum(v^2); added in warp order: deterministic.
+                // RMSNorm scale of this phase's input (th.cpp:1153-1200): every hand-off record carries the sixteen warps'
+                // shares of sum(v^2); added in warp order: deterministic.
                 float tot = 0.f;
 #pragma unroll
-                for (int w = 0; w < kMathWarps; ++w) tot += lds32f(S.red_a + (buf * kRedFloats + w * kRecFloats + kRows) * 4u);
+                for (int w = 0; w < kMathWarps; ++w) tot += lds32f(S.red_a + (buf * kRedFloats + w * kRecFloats + kHalf) * 4u);
                 scale = 1.0f / sqrtf(tot / (float)d.C + 1e-6f);
                 have_scale = true;
             }
@@ -1256,22 +1192,19 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
                     }
                     break;
                 case EPI_WO:                                                           // th-llama.cpp:409
-                    if (!kTP) { const float v = resid + y; p.h1[r] = v; if (p.dataflow) st_flagged(p.h1f + r, v, epoch); }
-                    else if (p.dataflow) for (int dst = 0; dst < tp_size; ++dst) st_flagged_sys(xbf_ptr(p, dst, 0, tp_rank) + r, y, epoch);
-                    else for (int dst = 0; dst < tp_size; ++dst) xb_ptr(p, dst, 0, tp_rank)[r] = y;   // partial -> every rank
+                    if (!kTP) st_flagged(p.h1f + r, resid + y, epoch);
+                    else for (int dst = 0; dst < tp_size; ++dst) st_flagged_sys(xbf_ptr(p, dst, 0, tp_rank) + r, y, epoch);   // partial -> every rank
                     break;
                 case EPI_W13:
                     if (sub == 0) es.gate = y;
                     else {                                                              // :436,:438
-                        const float gv = es.gate, v = (gv / (1.0f + expf(-gv))) * y;
-                        p.ff[r] = v;
-                        if (p.dataflow) st_flagged(p.fff + r, v, epoch);
+                        const float gv = es.gate;
+                        st_flagged(p.fff + r, (gv / (1.0f + expf(-gv))) * y, epoch);
                     }
                     break;
                 case EPI_W2:                                                           // th-llama.cpp:447
-                    if (!kTP) { const float v = resid + y; p.x[r] = v; if (p.dataflow) st_flagged(p.xf + r, v, epoch); }
-                    else if (p.dataflow) for (int dst = 0; dst < tp_size; ++dst) st_flagged_sys(xbf_ptr(p, dst, 1, tp_rank) + r, y, epoch);
-                    else for (int dst = 0; dst < tp_size; ++dst) xb_ptr(p, dst, 1, tp_rank)[r] = y;
+                    if (!kTP) { const float v = resid + y; p.x[r] = v; st_flagged(p.xf + r, v, epoch); }
+                    else for (int dst = 0; dst < tp_size; ++dst) st_flagged_sys(xbf_ptr(p, dst, 1, tp_rank) + r, y, epoch);
                     break;
                 default: {                                                             // EPI_OUT
                     if (p.logits) p.logits[r] = y;
@@ -1289,7 +1222,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
     const int lane = (int)threadIdx.x & 31;
     EpiState es{0.f, 0.f, -1};
     bool dead = false;
-    unsigned gq = 0, nbar = 0, xk = 0;
+    unsigned gq = 0, nbar = 0;
     // RoPE table for this token: cos/sin(n_past * 10000^(-2i/D)) (th.cpp:1478-1482), once per CTA
     for (int i = lane; i < (p.head_dim >> 1); i += 32) {
         const float theta = powf(10000.0f, (-(float)(2 * i)) / (float)p.head_dim);
@@ -1308,10 +1241,9 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
             bar_sync(BAR_PRE, kMathThreads + 32);
         }
         if (k == K_OUT) break;
-        if (!(p.dataflow && (k == K_WO || k == K_W13 || k == K_W2))) {
+        if (k == K_QKV || k == K_ATT) {
             ++nbar;
-            if (kTP && (k == K_WO || k == K_W2)) { ++xk; grid_barrier<kTP>(p, nbar, lane, dead, k == K_WO ? 0 : 1, p.epoch_base + xk); }
-            else grid_barrier<kTP>(p, nbar, lane, dead);
+            grid_barrier(p, nbar, lane, dead);
             bar_sync(BAR_ALL, kMathThreads + 32);
         }
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
@@ -1327,7 +1259,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
         }
         if (lane == 0) { p.amax_val[blockIdx.x] = bv; p.amax_idx[blockIdx.x] = bi; }
         ++nbar;
-        grid_barrier<kTP>(p, nbar, lane, dead);
+        grid_barrier(p, nbar, lane, dead);
         if (blockIdx.x == 0) {
             // every lane takes CTAs lane, lane+32, ... (loads in flight together), then the warp reduces
             float gv = 0.f; int gi = -1;
@@ -1352,7 +1284,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
             if (lane == 0) {
                 if (kTP) {
                     // cross-rank argmax: push this rank's candidate to every rank, wait for all, lowest id wins ties
-                    const unsigned epoch = p.epoch_base + 2u * (unsigned)p.n_layer + 1u;
+                    const unsigned epoch = p.epoch_base + 1u;
                     for (int d = 0; d < p.tp_size; ++d) { xamax_val(p, d)[p.tp_rank] = gv; xamax_idx(p, d)[p.tp_rank] = gi; }
                     __threadfence_system();
                     for (int d = 0; d < p.tp_size; ++d) st_release_sys(xflags(p, d, 1) + p.tp_rank, epoch);
@@ -1361,11 +1293,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
                     for (int src = 0; src < p.tp_size; ++src) {
                         const unsigned* f = xflags(p, p.tp_rank, 1) + src;
                         while ((int)(ld_acquire_sys(f) - epoch) < 0) {
-                            if ((++it & 63u) == 0u) {
-                                if (t0 == 0) t0 = gtimer();
-                                if (aborted(p)) break;
-                                if (gtimer() - t0 > p.timeout_ns) { raise_abort(p, 0x401u, (unsigned)src, epoch); break; }
-                            }
+                            if ((++it & 63u) == 0u && poll_watchdog(p.status, p.timeout_ns, t0, 0x401u, (unsigned)src, epoch)) break;
                         }
                         const int idx = __ldcv(xamax_idx(p, p.tp_rank) + src);
                         const float v = __ldcv(xamax_val(p, p.tp_rank) + src);
@@ -1380,9 +1308,68 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
     if (PROF(p) && lane == 0) prof_mark(PROF(p), 5u * (unsigned)p.n_layer + 1u, PROF_START);
 }
 
+// ------------------------------------------------------------------------------------------
+// REDUCER WARP (tensor parallel)
+// ------------------------------------------------------------------------------------------
+// The all-reduce after Wo and W2 (th-llama.cpp:402-409, 441-447 under Megatron-style sharding) in one NVLink hop plus one
+// local hop: every rank's epilogue pushed its partial rows into the slot [which][source rank] of every rank's exchange
+// region; here CTA b owns elements [E b / grid, E (b+1) / grid) of the residual stream, one or a few per lane, IN
+// REGISTERS for the whole token.  Per exchange a lane polls the tp partials of its elements (all loads in flight; the
+// epoch stamp makes the read the wait), adds them in rank order -- bitwise identical on every rank -- and publishes the
+// new residual value in the local flagged vector the next prologue (and nobody else) polls.
+__device__ void reducer_main(const DecParams& p, int tok) {
+    const int lane = (int)threadIdx.x & 31;
+    const int E = p.n_embd, tp = p.tp_size;
+    const int i0 = (int)(((long long)E * blockIdx.x) / gridDim.x), i1 = (int)(((long long)E * (blockIdx.x + 1)) / gridDim.x);
+    const uint16_t* emb_row = p.emb + (size_t)tok * E;
+    float resid[kMaxOwn];
+#pragma unroll
+    for (int j = 0; j < kMaxOwn; ++j) {
+        const int i = i0 + lane + 32 * j;
+        resid[j] = i < i1 ? __half2float(__ushort_as_half(__ldg(emb_row + i))) : 0.f;
+    }
+    const unsigned long long* xbf = (const unsigned long long*)p.xchg[p.tp_rank];
+    bool dead = false;
+    for (int l = 0; l < p.n_layer; ++l) {
+        const unsigned epoch = p.flag_epoch + (unsigned)l + 1u;
+        for (int which = 0; which < 2; ++which) {
+            unsigned long long* dstv = which == 0 ? p.h1f : p.xf;
+#pragma unroll
+            for (int j = 0; j < kMaxOwn; ++j) {
+                const int i = i0 + lane + 32 * j;
+                if (i >= i1) continue;
+                const unsigned long long* src = xbf + (size_t)which * tp * E + i;
+                unsigned long long e[8];
+                unsigned long long t0 = 0;
+                unsigned it = 0;
+                while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) if (r < tp) e[r] = ld_flagged1_sys(src + (size_t)r * E);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) if (r < tp && (unsigned)(e[r] >> 32) != epoch) ok = false;
+                    if (ok || dead || p.nosync) break;
+                    if ((++it & 63u) == 0u && poll_watchdog(p.status, p.timeout_ns, t0, 0x600u | (unsigned)which, (unsigned)i, epoch)) dead = true;
+                }
+                float v = resid[j];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) if (r < tp) v += __uint_as_float((unsigned)e[r]);
+                resid[j] = v;
+                st_flagged(dstv + i, v, epoch);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxOwn; ++j) {
+        const int i = i0 + lane + 32 * j;
+        if (i < i1) p.x[i] = resid[j];
+    }
+}
+
 template <bool kTP>
 __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_constant__ DecParams p) {
     const Smem S = smem_view();
+    const int tok = *p.token;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNumSlots; ++i) {
             mbar_init(S.full_a + i * 8, 1);
@@ -1393,24 +1380,27 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
             mbar_init(S.red_free_a + i * 8, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (blockIdx.x == 0) *p.bar_next = 0u;   // arm the next launch's barrier counter
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 69) {            // (a parked warp of the service group)
+    // A token id outside the vocabulary (th-llama.cpp:606 asserts) is the same on every CTA (and every rank): the whole
+    // grid leaves before any phase starts, nothing waits on anything, and the host reads THK_E_INVALID from the status word.
+    if (tok < 0 || tok >= p.n_vocab) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) raise_abort(p, 0x300u, (unsigned)tok, 0u);
+        return;
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 69) {            // (lanes of the reducer warp)
         const int ph = (int)threadIdx.x - 64;
         RowIt::share(p.ph[ph], gridDim.x, blockIdx.x, S.misc->range[ph][0], S.misc->range[ph][1]);
     }
     __syncthreads();
-    if (threadIdx.x < kMathBase) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
-        if (threadIdx.x < 32) producer_main(p, S);
-        else if (threadIdx.x < 64) epi_main<kTP>(p, S);
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMathRegs));
-        math_main<kTP>(p, S);
-    }
+    if (threadIdx.x < 32) producer_main(p, S);
+    else if (threadIdx.x < 64) epi_main<kTP>(p, S);
+    else if (threadIdx.x < kMathBase) { if (kTP) reducer_main(p, tok); }
+    else math_main(p, tok);
 }
 
-size_t decode_smem_bytes(int max_vec, int res_vec) {
-    return (size_t)kXsOffset + (size_t)((max_vec + 255) & ~255) * sizeof(float) + (size_t)((res_vec + 255) & ~255) * sizeof(float);
+size_t decode_smem_bytes(int max_vec) {
+    return (size_t)kXsOffset + (size_t)((max_vec + 255) & ~255) * sizeof(float);
 }
 
 PhaseDesc make_phase(int nseg, const int* rows, int C, bool paired) {
@@ -1418,7 +1408,7 @@ PhaseDesc make_phase(int nseg, const int* rows, int C, bool paired) {
     d.C = C; d.nseg = nseg; d.paired = paired ? 1 : 0;
     for (int i = 0; i < 3; ++i) d.rows[i] = i < nseg ? rows[i] : 0;
     const int chunks = (C + 255) / 256;
-    d.KT = (chunks + kMathWarps - 1) / kMathWarps;
+    d.KT = (chunks + kChunks - 1) / kChunks;
     d.CT = ((chunks + d.KT - 1) / d.KT) * 256;          // K split evenly over the tiles
     return d;
 }
@@ -1463,11 +1453,55 @@ static int check_status(thk_decoder* d) {
     THK_CUDA(cudaMemcpyAsync(st, d->p.status, sizeof st, cudaMemcpyDeviceToHost, d->ctx->stream));
     THK_CUDA(cudaStreamSynchronize(d->ctx->stream));
     if (st[0] != 0) {
-        thk_set_error("decode kernel aborted: code 0x%x a=%u b=%u cta=%u (0x1xx mbarrier wait, 0x200 grid barrier, 0x300 bad token)",
-                      st[0], st[1], st[2], st[3]);
+        thk_set_error("decode kernel aborted: code 0x%x a=%u b=%u cta=%u (0x1xx mbarrier wait, 0x200 grid barrier, 0x300 bad token, 0x4xx argmax exchange, "
+                      "0x5xx flagged vector, 0x6xx tensor-parallel partials)", st[0], st[1], st[2], st[3]);
         cudaMemsetAsync(d->p.status, 0, sizeof st, d->ctx->stream);
         return st[0] == 0x300u ? THK_E_INVALID : THK_E_TIMEOUT;
     }
+    return THK_OK;
+}
+
+extern "C" int thk_decoder_destroy(thk_decoder* d) {
+    if (!d) return THK_OK;
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    cudaFree(d->d_layers); cudaFree(d->scratch); cudaFree(d->flagged); cudaFree(d->ctrl); cudaFree(d->d_tok); cudaFree(d->d_prof); cudaFree(d->xchg);
+    delete d;
+    return THK_OK;
+}
+
+static int decoder_alloc(thk_decoder* d, const thk_llama_layer* layers) {
+    DecParams& p = d->p;
+    const int tp = p.tp_size, D = p.head_dim;
+    if (tp > 1) THK_CUDA(cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+    else THK_CUDA(cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+    THK_CUDA(cudaMalloc(&d->d_layers, sizeof(thk_llama_layer) * p.n_layer));
+    THK_CUDA(cudaMemcpy(d->d_layers, layers, sizeof(thk_llama_layer) * p.n_layer, cudaMemcpyHostToDevice));
+    p.layers = d->d_layers;
+    // scratch: x [E]; q [Eh]; part [Hl*S*(D+4)] split-KV results {m, l, -, -, o[D]}; amax [grid] x2
+    const size_t part_n = (size_t)p.Hl * p.att_max_split * (D + 4);
+    const size_t nfl = (size_t)p.n_embd + p.Eh + part_n + 2 * d->grid + 64;
+    THK_CUDA(cudaMalloc(&d->scratch, nfl * sizeof(float)));
+    THK_CUDA(cudaMemset(d->scratch, 0, nfl * sizeof(float)));
+    float* f = d->scratch;
+    p.x = f; f += p.n_embd; p.q = f; f += p.Eh;
+    p.part = f; f += part_n; p.amax_val = f; f += d->grid; p.amax_idx = (int*)f;
+    const size_t nflag = (size_t)2 * p.n_embd + (size_t)((p.Fh + 1) & ~1);
+    THK_CUDA(cudaMalloc(&d->flagged, nflag * sizeof(unsigned long long)));
+    THK_CUDA(cudaMemset(d->flagged, 0, nflag * sizeof(unsigned long long)));     // epoch 0 is never used
+    p.h1f = d->flagged; p.xf = p.h1f + p.n_embd; p.fff = p.xf + p.n_embd;
+    const size_t nctrl = 64 + 4;
+    THK_CUDA(cudaMalloc(&d->ctrl, nctrl * sizeof(unsigned)));
+    THK_CUDA(cudaMemset(d->ctrl, 0, nctrl * sizeof(unsigned)));
+    p.status = d->ctrl + 64;
+    THK_CUDA(cudaMalloc(&d->d_tok, sizeof(int) * 2));
+    if (tp > 1) {
+        d->xchg_bytes = ((size_t)2 * tp * p.n_embd * sizeof(unsigned long long) + (size_t)4 * tp * sizeof(unsigned) + 255) & ~(size_t)255;
+        THK_CUDA(cudaMalloc(&d->xchg, d->xchg_bytes));
+        THK_CUDA(cudaMemset(d->xchg, 0, d->xchg_bytes));
+        p.xchg[p.tp_rank] = d->xchg;
+    }
+    THK_CUDA(cudaDeviceSynchronize());
     return THK_OK;
 }
 
@@ -1483,7 +1517,10 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     THK_CHECK_ARG(D % 16 == 0 && D <= kMaxHeadDim, "head_dim %d unsupported (need a multiple of 16, <= %d)", D, kMaxHeadDim);
     THK_CHECK_ARG(dims->n_embd % 8 == 0 && dims->n_ff % 8 == 0, "n_embd and n_ff must be multiples of 8 (16-byte f16 rows)");
     THK_CHECK_ARG(dims->n_head % tp == 0 && dims->n_ff % tp == 0 && dims->n_vocab % tp == 0, "tp_size must divide n_head, n_ff, n_vocab");
+    THK_CHECK_ARG((dims->n_ff / tp) % 8 == 0, "n_ff / tp_size = %d must be a multiple of 8 (16-byte rows of the W2 shard)", dims->n_ff / tp);
     THK_CHECK_ARG(dims->n_ctx > 0 && dims->n_layer > 0 && dims->n_vocab > 0, "bad dims");
+    THK_CHECK_ARG(dims->n_layer <= 254, "n_layer %d unsupported (epoch-stamped vectors encode the layer in 8 bits)", dims->n_layer);
+    THK_CHECK_ARG(tp == 1 || dims->n_embd <= 32 * kMaxOwn * ctx->sm_count, "n_embd %d too large for the tensor-parallel reducer (<= %d)", dims->n_embd, 32 * kMaxOwn * ctx->sm_count);
     THK_CUDA(cudaSetDevice(ctx->device));
 
     thk_decoder* d = new thk_decoder;
@@ -1507,57 +1544,18 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     p.timeout_ns = 4000000000ull;
     p.prof_phase = -1;
     // tuning knobs (defaults = the measured best)
-    p.l2_ahead = (unsigned)(getenv("THK_L2_AHEAD_KB") ? atoi(getenv("THK_L2_AHEAD_KB")) : 64) * 1024u;   // 0 / 64 / 128 / 192 KB: 2.765 / 2.720 / 2.744 / 2.767 ms
+    p.l2_ahead = (unsigned)(getenv("THK_L2_AHEAD_KB") ? atoi(getenv("THK_L2_AHEAD_KB")) : 64) * 1024u;
+    p.poll_single = getenv("THK_POLL_SINGLE") ? atoi(getenv("THK_POLL_SINGLE")) : 1;
     const int max_vec = p.n_embd > p.Fh ? p.n_embd : p.Fh;
-    d->smem = decode_smem_bytes(max_vec, tp > 1 ? p.n_embd : 0);
-    p.res_off = (unsigned)(((max_vec + 255) & ~255) * sizeof(float));
+    d->smem = decode_smem_bytes(max_vec);
     if (d->smem > 227 * 1024) {
         thk_set_error("thk_decoder_create: needs %zu bytes of shared memory (> 227 KB); n_ff/tp=%d too large", d->smem, p.Fh);
         delete d;
         return THK_E_UNSUPPORTED;
     }
-    if (tp > 1) THK_CUDA(cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
-    else THK_CUDA(cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
-
-    THK_CUDA(cudaMalloc(&d->d_layers, sizeof(thk_llama_layer) * p.n_layer));
-    THK_CUDA(cudaMemcpy(d->d_layers, layers, sizeof(thk_llama_layer) * p.n_layer, cudaMemcpyHostToDevice));
-    p.layers = d->d_layers;
-    // scratch: x, h1 [E]; q [Eh]; ff [Fh]; part [Hl*S*(D+4)] split-KV results {m, l, -, -, o[D]}; amax [grid] x2
-    const size_t part_n = (size_t)p.Hl * p.att_max_split * (D + 4);
-    const size_t nfl = (size_t)2 * p.n_embd + p.Eh + p.Fh + part_n + 2 * d->grid + 64;
-    THK_CUDA(cudaMalloc(&d->scratch, nfl * sizeof(float)));
-    THK_CUDA(cudaMemset(d->scratch, 0, nfl * sizeof(float)));
-    float* f = d->scratch;
-    p.x = f; f += p.n_embd; p.h1 = f; f += p.n_embd; p.q = f; f += p.Eh;
-    p.ff = f; f += (p.Fh + 3) & ~3; p.part = f; f += part_n; p.amax_val = f; f += d->grid; p.amax_idx = (int*)f;
-    const size_t nflag = (size_t)2 * p.n_embd + (size_t)((p.Fh + 1) & ~1);
-    THK_CUDA(cudaMalloc(&d->flagged, nflag * sizeof(unsigned long long)));
-    THK_CUDA(cudaMemset(d->flagged, 0, nflag * sizeof(unsigned long long)));     // epoch 0 is never used
-    p.h1f = d->flagged; p.xf = p.h1f + p.n_embd; p.fff = p.xf + p.n_embd;
-    p.dataflow = (p.n_layer <= 254 && !(getenv("THK_DATAFLOW") && atoi(getenv("THK_DATAFLOW")) == 0)) ? 1 : 0;
-    p.poll_single = getenv("THK_POLL_SINGLE") ? atoi(getenv("THK_POLL_SINGLE")) : 1;
-    const size_t nctrl = 64 + 4;
-    THK_CUDA(cudaMalloc(&d->ctrl, nctrl * sizeof(unsigned)));
-    THK_CUDA(cudaMemset(d->ctrl, 0, nctrl * sizeof(unsigned)));
-    p.status = d->ctrl + 64;
-    THK_CUDA(cudaMalloc(&d->d_tok, sizeof(int) * 2));
-    if (tp > 1) {
-        d->xchg_bytes = ((size_t)2 * tp * p.n_embd * sizeof(unsigned long long) + (size_t)4 * tp * sizeof(unsigned) + 255) & ~(size_t)255;
-        THK_CUDA(cudaMalloc(&d->xchg, d->xchg_bytes));
-        THK_CUDA(cudaMemset(d->xchg, 0, d->xchg_bytes));
-        p.xchg[p.tp_rank] = d->xchg;
-    }
-    THK_CUDA(cudaDeviceSynchronize());
+    const int rc = decoder_alloc(d, layers);
+    if (rc != THK_OK) { thk_decoder_destroy(d); return rc; }     // one cleanup path: frees whatever was allocated
     *out = d;
-    return THK_OK;
-}
-
-extern "C" int thk_decoder_destroy(thk_decoder* d) {
-    if (!d) return THK_OK;
-    cudaSetDevice(d->ctx->device);
-    cudaStreamSynchronize(d->ctx->stream);
-    cudaFree(d->d_layers); cudaFree(d->scratch); cudaFree(d->flagged); cudaFree(d->ctrl); cudaFree(d->d_tok); cudaFree(d->d_prof); cudaFree(d->xchg);
-    delete d;
     return THK_OK;
 }
 
@@ -1565,13 +1563,12 @@ static int launch_step(thk_decoder* d, const int32_t* token, int32_t n_past, flo
     THK_ENTER(d->ctx);
     DecParams p = d->p;
     p.token = token; p.n_past = n_past; p.logits = logits; p.next_token = next_token; p.next_logit = next_logit;
-    // tensor parallel: the end-of-launch argmax exchange is also what keeps a fast rank's NEXT launch from overwriting
-    // exchange records a slow rank still reads -- make sure it always runs
-    if (p.tp_size > 1 && !p.next_token && !p.next_logit) p.next_token = d->d_tok + 1;
     if (p.tp_size > 1) {
         if (!d->peers_set) { thk_set_error("thk_decoder_step: tensor-parallel decoder has no peers (call thk_decoder_set_peers)"); return THK_E_INVALID; }
+        // the end-of-launch argmax exchange always runs: every rank embeds the token the ranks agreed on
+        if (!p.next_token && !p.next_logit) p.next_token = d->d_tok + 1;
         p.epoch_base = d->epoch;
-        d->epoch += 2u * (unsigned)p.n_layer + 2u;
+        d->epoch += 2u;
     }
     p.flag_epoch = (++d->flag_seq) << 8;                 // layer l of this launch stamps its vectors with flag_epoch + l + 1
     p.bar_ctr = d->ctrl + (d->launch_seq % 64);
@@ -1639,9 +1636,9 @@ extern "C" int thk_decoder_tune(thk_decoder* d, const char* key, int value) {
     THK_CHECK_ARG(d && key, "thk_decoder_tune: null argument");
     if (!strcmp(key, "l2_ahead_kb")) { THK_CHECK_ARG(value >= 0 && value <= 1024, "l2_ahead_kb out of range"); d->p.l2_ahead = (unsigned)value * 1024u; }
     else if (!strcmp(key, "prof_phase")) d->p.prof_phase = value;
-    else if (!strcmp(key, "dataflow")) { THK_CHECK_ARG(value == 0 || d->p.n_layer <= 254, "dataflow needs n_layer <= 254"); d->p.dataflow = value != 0; }
     else if (!strcmp(key, "poll_single")) d->p.poll_single = value != 0;
     else if (!strcmp(key, "nosync")) d->p.nosync = value != 0;
+    else if (!strcmp(key, "timeout_ms")) { THK_CHECK_ARG(value > 0, "timeout_ms must be positive"); d->p.timeout_ns = (unsigned long long)value * 1000000ull; }
     else { thk_set_error("thk_decoder_tune: unknown key %s", key); return THK_E_INVALID; }
     return THK_OK;
 }

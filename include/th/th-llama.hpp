@@ -94,6 +94,10 @@ struct LlamaModel {                  // th-llama.hpp:100-177
     // ---- CUDA engine state (no reference analogue) ----
     WGPUDevice device{};
     EvalPath evalPath = EvalPath_Fused;
+    // The two evaluation paths keep the KV cache in different layouts ([pos][head][dim] as in th-llama-loader.cpp:335 for
+    // the op graph, [head][pos][dim] for the fused kernel).  Number of leading positions valid in each; th_eval_gpu
+    // copies the missing rows across before it evaluates, so the paths can be mixed freely within one context.
+    int32_t kvValidPhd = 0, kvValidHpd = 0;
     float samplerTemp = 0.0f;        // reference hard-codes 0.8 (th-llama.cpp:721); greedy is the parity mode
     thk_decoder* decoder = nullptr;
     int32_t* d_token = nullptr;      // device: token id in, greedy id out

@@ -124,6 +124,9 @@ int thk_f16_f32_conversion(thk_ctx* ctx, float* out, size_t out_offset_bytes, co
 /* KV rows [pos0, pos0+npos) from the op graph's [pos][head][dim] cache into the fused decoder's
  * [head][n_ctx][dim] cache (hand-over from batched prefill to single-token decode) */
 int thk_kv_to_hpd(thk_ctx* ctx, const float* src_phd, float* dst_hpd, int64_t pos0, int64_t npos, int64_t n_ctx, int64_t H, int64_t D);
+/* ... and back, so that the op graph / a batched pass can continue a context the fused decoder extended (one
+ * authoritative cache per position: th_eval_gpu tracks which layout holds which rows) */
+int thk_kv_from_hpd(thk_ctx* ctx, const float* src_hpd, float* dst_phd, int64_t pos0, int64_t npos, int64_t n_ctx, int64_t H, int64_t D);
 
 /* ---- synthetic tensors (no reference analogue): same counter PRNG as the oracle ---- */
 int thk_fill_f16(thk_ctx* ctx, uint16_t* dst, uint64_t seed, uint64_t tensor_id, int64_t rows, int64_t cols,

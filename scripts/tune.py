@@ -73,6 +73,14 @@ def main():
                 brief = {k: {kk: round(vv, 2) for kk, vv in v.items() if kk in ("us", "arrive_skew_us", "barrier_latency_us", "prologue_us", "first_tile_wait_us", "tile_span_med_us", "tile_span_max_us")}
                          for k, v in s.items() if isinstance(v, dict)}
                 print("PHASES", tag, json.dumps(brief), "kernel_us", round(s["kernel_us"], 1), flush=True)
+                w = model.last_wait_cycles.astype(float)
+                life = w[:, :, 3].clip(min=1)
+                import numpy as np
+                names = ["ring", "handoff", "poll"]
+                for role, sl in (("math", slice(0, 16)), ("producer", slice(16, 17)), ("epilogue", slice(17, 18))):
+                    fr = [float(np.median(w[:, sl, i] / life[:, sl])) for i in range(3)]
+                    print(f"WAITS {tag} {role:9s} lifetime {np.median(life[:, sl])/1e6:6.3f} Mcycles; share waiting: "
+                          + ", ".join(f"{n} {100*f:5.1f}%" for n, f in zip(names, fr)), flush=True)
     results.sort()
     print("BEST", results[0][1], f"{results[0][0]:.4f} ms  {1e3/results[0][0]:.1f} tok/s")
     model.close()

@@ -38,16 +38,21 @@
 namespace {
 
 constexpr int kSlotBytes = 32 * 1024;
-constexpr int kNumSlots = 4;                          // measured on B200: 3 -> 2.83, 4 -> 2.72, 5 -> 2.75 ms/token (deeper rings queue more
-                                                      // traffic ahead of the latency-critical barrier / prologue loads)
+constexpr int kNumSlots = 5;                          // two tiles are being consumed at any time (one per warp group), three are in flight
 constexpr int kChunks = 8;                            // 256-column chunks per tile
-constexpr int kMathWarps = 16;                        // (chunk, row half)
+constexpr int kGroupWarps = 8;                        // warps per consumer group: one per chunk
+constexpr int kGroups = 2;                            // consumer groups; tile t of the CTA's stream belongs to group t % 2
+constexpr int kMathWarps = kGroups * kGroupWarps;     // (group, chunk)
 constexpr int kMathThreads = kMathWarps * 32;
 constexpr int kSvcWarps = 3;                          // producer, epilogue, reducer
-constexpr int kMathBase = kSvcWarps * 32;
-constexpr int kThreads = kMathBase + kMathThreads;    // 608 -> 104 registers per thread, no setmaxnreg, out-of-line slow paths allowed
+#ifdef THK_SVC_FIRST                                  // (A/B variant: service warps on the lowest warp ids)
+constexpr int kMathBase = kSvcWarps * 32, kSvcBase = 0;
+#else
+constexpr int kMathBase = 0;                          // math warps 0-15; the service warps take the HIGHEST warp ids: the warp scheduler
+constexpr int kSvcBase = kMathThreads;                // prefers high warp ids, and producer / epilogue must never wait behind four busy math warps
+#endif
+constexpr int kThreads = kMathThreads + kSvcWarps * 32;   // 608 threads: 96 registers each (warps are allocated in fours), no setmaxnreg
 constexpr int kRows = 8;                              // rows per row group (= per tile)
-constexpr int kHalf = 4;                              // rows per math warp
 constexpr int kMaxTilePos = 128;                      // attention: positions per tile cap
 constexpr int kMaxHeadDim = 128;
 constexpr int kMaxSplit = 8;                          // attention: KV splits per head cap
@@ -283,13 +288,18 @@ struct SmemMisc {
     unsigned long long red_free[kDumpBufs];   // ... and consumed by the epilogue warp
     float2 rope[kMaxHeadDim / 2];       // (cos, sin) of n_past * theta_i for this token
     int range[5][2];                    // this CTA's row range [r, r_end) of every matvec phase (computed once per launch)
+    DecParams prm;                      // the kernel parameters for the out-of-line phase functions of the math warps (a reference to the
+                                        // __grid_constant__ parameter would turn every field access into a global load)
+    unsigned long long wstat[kMathWarps + kSvcWarps][4];   // -DTHK_PROFILE: cycles a warp spent waiting, see WaitSlot
 };
-constexpr int kMiscBytes = 1024;
+constexpr int kMiscBytes = 2048;
 static_assert(sizeof(SmemMisc) <= kMiscBytes, "SmemMisc too large");
-constexpr int kRecFloats = kHalf + 1;                          // per warp: 4 row sums + its share of sum(v^2) of the phase input
+static_assert(sizeof(DecParams) % 4 == 0, "DecParams is copied word by word");
+constexpr int kRecFloats = kRows + 1;                          // per warp: 8 row sums + its share of sum(v^2) of the phase input
+constexpr int kRecArrivals = kRows + 1;                        // every lane that writes a record word arrives itself (no __syncwarp)
 constexpr int kRedFloats = kMathWarps * kRecFloats;            // one row-group hand-off record
 constexpr int kAttScratchOff = kDumpBufs * kRedFloats;         // attention scratch (floats) behind the hand-off ring
-constexpr int kRedBytes = 12 * 1024;                           // ring (2.5 KB) + attention scratch (<= 9.2 KB)
+constexpr int kRedBytes = 14 * 1024;                           // ring (4.5 KB) + attention scratch (<= 9.2 KB)
 static_assert(kAttScratchOff * 4 + (kMathWarps * kMaxHeadDim + 2 * kMathWarps + 2 * kMaxHeadDim) * 4 <= kRedBytes, "attention scratch does not fit");
 constexpr int kXsOffset = kNumSlots * kSlotBytes + kMiscBytes + kRedBytes;
 
@@ -324,30 +334,78 @@ __device__ __forceinline__ Smem smem_view() {
     return carve(smem_base);
 }
 
+// -DTHK_PROFILE: who waits for whom.  Every warp accumulates (lane 0, in shared memory) the cycles it spent in the slow
+// path of its waits and copies its four counters to the timeline buffer when it finishes.
+enum WaitSlot { WS_RING = 0,     // math: ring slot not full yet; producer: no empty slot; epilogue: no row group handed over yet
+                WS_HANDOFF = 1,  // math: hand-off record not consumed yet; epilogue: residual operand (flagged vector)
+                WS_POLL = 2,     // math: prologue (flagged vector / staging); epilogue: grid barrier
+                WS_TOTAL = 3 };  // lifetime of the warp
+constexpr int kProfWarps = kMathWarps + kSvcWarps;
+#ifdef THK_PROFILE
+__device__ __forceinline__ long long wstat_t0() { return clock64(); }
+__device__ __forceinline__ void wstat_add(int slot, long long t0) {
+    if ((threadIdx.x & 31) == 0) smem_view().misc->wstat[threadIdx.x >> 5][slot] += (unsigned long long)(clock64() - t0);
+}
+__device__ __noinline__ void wstat_flush(unsigned long long* prof, long long t_start) {
+    if ((threadIdx.x & 31) != 0 || prof == nullptr) return;
+    SmemMisc* misc = smem_view().misc;
+    const int w = threadIdx.x >> 5;
+    misc->wstat[w][WS_TOTAL] = (unsigned long long)(clock64() - t_start);
+    unsigned long long* dst = prof + (size_t)gridDim.x * (kProfPhases * 8 + 4 + 2 * kProfTiles) + ((size_t)blockIdx.x * kProfWarps + w) * 4;
+    for (int i = 0; i < 4; ++i) dst[i] = misc->wstat[w][i];
+}
+#else
+__device__ __forceinline__ long long wstat_t0() { return 0; }
+__device__ __forceinline__ void wstat_add(int, long long) {}
+__device__ __forceinline__ void wstat_flush(unsigned long long*, long long) {}
+#endif
+
 // activation layout in xs: 256-col chunk c, lane l owns cols 8l..8l+7; its first float4 (cols 8l..8l+3) sits at
 // (c*64 + l)*16 B and its second at (c*64 + 32 + l)*16 B -- consecutive lanes hit consecutive banks (conflict free).
 // A chunk's values are staged by the two warps that own the chunk (K tiles alternate between them) and read by both.
 
 // ring position shared by producer and consumers (kept incrementally: no modulo per tile)
 struct Ring {
-    uint32_t sl, par;
-    __device__ __forceinline__ void advance() { if (++sl == kNumSlots) { sl = 0; par ^= 1u; } }
+    uint32_t sl, par, odd;      // slot, phase parity of its barriers, parity of the tile counter (consumer group that owns the tile)
+    __device__ __forceinline__ void advance() { odd ^= 1u; if (++sl == kNumSlots) { sl = 0; par ^= 1u; } }
 };
 
 // per-thread consumer state
 struct Cons {
     Ring ring;
     bool dead;            // watchdog fired somewhere: stop waiting, keep walking the schedule
+    bool ready;           // the group's NEXT tile was already seen complete by the look-ahead test_wait
 };
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {      // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void wait_full(const DecParams& p, const Smem& S, Cons& c, unsigned tag) {
     if (c.dead) return;
     const uint32_t bar = S.full_a + c.ring.sl * 8;
-    if (!mbar_try_wait(bar, c.ring.par)) c.dead = !mbar_wait_slow(p.status, p.timeout_ns, bar, c.ring.par, tag);
+    if (!mbar_try_wait(bar, c.ring.par)) {
+        const long long t0 = wstat_t0();
+        c.dead = !mbar_wait_slow(p.status, p.timeout_ns, bar, c.ring.par, tag);
+        wstat_add(WS_RING, t0);
+    }
 }
 __device__ __forceinline__ void release_slot(const Smem& S, Cons& c, int lane) {
     __syncwarp();
     if (lane == 0) mbar_arrive(S.empty_a + c.ring.sl * 8);
     c.ring.advance();
+}
+// Look-ahead for this group's next tile (two tiles on): a NON-blocking test, issued right after the current tile's
+// shared loads so that its ~100+ cycles of latency hide behind the tile's math.  (The blocking try_wait costs 135-400
+// cycles per tile on the consumer's serial path even when the tile landed long ago: ncu, profiles/v5a.)
+__device__ __forceinline__ bool peek_tile_after_next(const Smem& S, const Cons& c) {
+    uint32_t sl = c.ring.sl + 2u, par = c.ring.par;
+    if (sl >= (uint32_t)kNumSlots) { sl -= (uint32_t)kNumSlots; par ^= 1u; }
+    return mbar_test_wait(S.full_a + sl * 8, par);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -420,6 +478,7 @@ __device__ __forceinline__ void wait_empty(const DecParams& p, const Smem& S, Pr
         const long long t0 = PROF(p) ? clock64() : 0;
         c.dead = !mbar_wait_slow(p.status, p.timeout_ns, bar, c.ring.par ^ 1u, tag);
         if (PROF(p)) c.wait_cyc += clock64() - t0;
+        wstat_add(WS_RING, t0);
     }
 }
 
@@ -511,7 +570,7 @@ __device__ __forceinline__ int phase_of(int k) { return k == K_QKV ? PH_QKV : k 
 
 __device__ void producer_main(const DecParams& p, const Smem& S) {
     const long long t0 = clock64();
-    Prod c{{0u, 0u}, false, 0u, 0, l2_evict_first_policy()};
+    Prod c{{0u, 0u, 0u}, false, 0u, 0, l2_evict_first_policy()};
     const int nsteps = 5 * p.n_layer + 1;
     int l = 0, k = K_QKV;                                 // same step order as the consumers
     for (int i = 0; i < nsteps; ++i) {
@@ -532,6 +591,7 @@ __device__ void producer_main(const DecParams& p, const Smem& S) {
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         stt[0] = (unsigned long long)c.wait_cyc; stt[1] = (unsigned long long)(clock64() - t0); stt[2] = c.tiles; stt[3] = smid;
     }
+    wstat_flush(PROF(p), t0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -560,152 +620,160 @@ __device__ __forceinline__ void fma8(const uint4& w, const unsigned long long* x
     acc = ffma2(x[3], cvt2(w.w), acc);
 }
 
-// Hand the four row sums of a finished row group to the epilogue warp.  A transposing shuffle reduction (2 + 1 exchanges
-// halve the rows a lane holds while doubling the lanes summed, then 3 plain steps) leaves the warp total of row lane >> 3
-// in every lane; 4 floats per warp go into a ring of kDumpBufs hand-off records, so the math warps can run kDumpBufs row
-// groups ahead of the epilogue warp.  Fixed order of additions: deterministic.  Called one tile AFTER the group's last
-// tile, between that tile's shared loads and its math, so the shuffle latency overlaps the load latency.
-__device__ __forceinline__ void flush_group(const DecParams& p, const Smem& S, Cons& c, unsigned& gq, float (&v)[kHalf], float ss,
+// Hand the eight row sums of a finished row group to the epilogue warp.  A transposing shuffle reduction (4 + 2 + 1
+// exchanges halve the rows a lane holds while doubling the lanes summed, then 2 plain steps) leaves the warp total of row
+// (lane >> 2) & 7 in every lane; 8 floats per warp go into a ring of kDumpBufs hand-off records, so the math warps can run
+// kDumpBufs row groups ahead of the epilogue warp.  Fixed order of additions: deterministic.  `real` == false: this warp
+// owned no tile of the row group (its group's turn fell on other row groups): zeros, no reduction.  Every lane that
+// writes a word of the record arrives on the record's barrier itself, so no __syncwarp is needed.
+// Called one tile AFTER the group's last tile, between that tile's shared loads and its math, so the shuffle latency
+// overlaps the load latency.
+__device__ __forceinline__ void flush_group(const DecParams& p, const Smem& S, Cons& c, unsigned& gq, float (&v)[kRows], bool real, float ss,
                                             uint32_t dump_a, int lane) {
-    const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0;
+    if (real) {
+        const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const float recv = __shfl_xor_sync(0xffffffffu, u4 ? v[r] : v[r + 2], 16);
-        v[r] = (u4 ? v[r + 2] : v[r]) + recv;
+        for (int r = 0; r < 4; ++r) {
+            const float recv = __shfl_xor_sync(0xffffffffu, u4 ? v[r] : v[r + 4], 16);
+            v[r] = (u4 ? v[r + 4] : v[r]) + recv;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float recv = __shfl_xor_sync(0xffffffffu, u3 ? v[r] : v[r + 2], 8);
+            v[r] = (u3 ? v[r + 2] : v[r]) + recv;
+        }
+        const float recv = __shfl_xor_sync(0xffffffffu, u2 ? v[0] : v[1], 4);
+        v[0] = (u2 ? v[1] : v[0]) + recv;
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    } else {
+        v[0] = 0.f;
     }
-    {
-        const float recv = __shfl_xor_sync(0xffffffffu, u3 ? v[0] : v[1], 8);
-        v[0] = (u3 ? v[1] : v[0]) + recv;
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 4);
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
     const unsigned buf = gq & (kDumpBufs - 1), use = gq / kDumpBufs;
     if (use > 0 && !c.dead) {
         const uint32_t fb = S.red_free_a + buf * 8;
-        if (!mbar_try_wait(fb, (use - 1) & 1u)) c.dead = !mbar_wait_slow(p.status, p.timeout_ns, fb, (use - 1) & 1u, 6);
+        if (!mbar_try_wait(fb, (use - 1) & 1u)) {
+            const long long t0 = wstat_t0();
+            c.dead = !mbar_wait_slow(p.status, p.timeout_ns, fb, (use - 1) & 1u, 6);
+            wstat_add(WS_HANDOFF, t0);
+        }
     }
-    if ((lane & 7) == 0) sts32f(dump_a + (buf * kRedFloats + (unsigned)(lane >> 3)) * 4u, v[0]);
-    if (lane == 1) sts32f(dump_a + (buf * kRedFloats + kHalf) * 4u, ss);          // this warp's share of sum(v^2) (norm phases)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(S.red_full_a + buf * 8);
+    const uint32_t rb = S.red_full_a + buf * 8;
+    if ((lane & 3) == 0) { sts32f(dump_a + (buf * kRedFloats + (unsigned)((lane >> 2) & 7)) * 4u, v[0]); mbar_arrive(rb); }
+    if (lane == 1) { sts32f(dump_a + (buf * kRedFloats + kRows) * 4u, ss); mbar_arrive(rb); }      // this warp's share of sum(v^2) (norm phases)
     ++gq;
 }
 
 // consumer state carried from phase to phase: row groups handed over so far and the ring position
-struct MState { unsigned gq, ring; };                          // ring = slot | parity << 8
 __device__ __forceinline__ unsigned long long pack_state(unsigned gq, const Ring& r) {
-    return ((unsigned long long)(r.sl | (r.par << 8)) << 32) | gq;
+    return ((unsigned long long)(r.sl | (r.par << 8) | (r.odd << 16)) << 32) | gq;
 }
 __device__ __forceinline__ void unpack_state(unsigned long long st, unsigned& gq, Ring& r) {
     gq = (unsigned)st;
     r.sl = (unsigned)(st >> 32) & 0xffu;
     r.par = (unsigned)(st >> 40) & 1u;
-}
-// this lane's activations of a phase with <= 2 K tiles, from xs into registers (packed for FFMA2; zero past the end)
-__device__ __forceinline__ void load_xr(const Smem& S, const PhaseDesc& d, int cw, int lane, unsigned long long (&xr)[8]) {
-    const int lcol = (cw << 8) + (lane << 3);
-    const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
-#pragma unroll
-    for (int kt = 0; kt < 2; ++kt) {
-        const int c = kt * d.CT + lcol;
-        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-        if (kt < d.KT && lcol < d.CT && c < d.C) {
-            x0 = lds128f(xa + (uint32_t)((kt * d.CT) << 2));
-            x1 = lds128f(xa + (uint32_t)((kt * d.CT) << 2) + 512u);
-        }
-        xr[kt * 4] = pack2(x0.x, x0.y); xr[kt * 4 + 1] = pack2(x0.z, x0.w);
-        xr[kt * 4 + 2] = pack2(x1.x, x1.y); xr[kt * 4 + 3] = pack2(x1.z, x1.w);
-    }
+    r.odd = (unsigned)(st >> 48) & 1u;
 }
 
-// Stream this CTA's tiles of one matvec phase.  Per tile a warp owns rows 4h..4h+3 of one 256-column chunk (rows past a
-// short group's end hold stale bytes; their sums are never read).  `gq` counts the row groups handed to the epilogue
-// warp since kernel start (hand-off record = gq % kDumpBufs).  XREG: the phase has <= 2 K tiles and this lane's
-// activations (packed for FFMA2; zero for columns past the end) stay in registers; else they are re-read from xs.
-// Out of line on purpose: the function gets its own register allocation (the 16 math warps leave 96 registers per
-// thread), so phase-level state of the caller is parked across the call instead of spilling inside the tile loop.
+// Stream this CTA's tiles of one matvec phase.  The 16 math warps form two groups of 8; tile t of the CTA's tile stream
+// (all phases, counted from kernel start) is consumed by group t % 2 ALONE -- so two tiles are in progress at any time and
+// a tile's serial chain (wait, shared loads, convert, FMA, release, row-group reduction) of one group hides behind the
+// other group's.  Within its tile a warp owns one 256-column chunk of all 8 rows (rows past a short group's end hold
+// stale bytes; their sums are never read): ten (XREG: eight) 128-bit shared loads by shared-window address, exact
+// f16 -> f32 conversion, packed FFMA2.  Every warp hands its partial row sums -- the K tiles its group owned -- to the
+// epilogue warp once per row group (`gq` counts them since kernel start; hand-off record = gq % kDumpBufs).
+// XREG: the phase has <= 2 K tiles, so a group owns the same K tile of every row group and this lane's 8 activations of
+// that tile (packed for FFMA2; zero for columns past the end) stay in registers; else they are re-read from xs.
+// Out of line on purpose: the function gets its own register allocation (19 warps leave 96 registers per thread), so
+// phase-level state of the caller is parked across the call instead of spilling inside the tile loop.
 template <bool XREG>
 __device__ __noinline__ unsigned long long math_mat_phase(const DecParams& p, int ph, unsigned long long state, float ss, unsigned phase_idx) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw >> 1, rh = mw & 1;
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1);
+    const unsigned g = (unsigned)(mw >> 3);
     unsigned long long* const pm = (PROF(p) != nullptr && ct == 0) ? PROF(p) + (size_t)blockIdx.x * kProfPhases * 8 : nullptr;
-    Cons c{{0u, 0u}, false};
+    Cons c{{0u, 0u, 0u}, false, false};
     unsigned gq;
     unpack_state(state, gq, c.ring);
     const PhaseDesc& d = p.ph[ph];
     const int C = d.C, KT = d.KT, CT = d.CT, nsub = d.paired ? 2 : 1;
     const int col = (cw << 8) + (lane << 3);                                  // this lane's first column inside a tile
     const uint32_t xlane_a = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);   // + col0 * 4: first float4; second 512 B on
-    const uint32_t dump_a = S.red_a + (uint32_t)((cw * 2 + rh) * kRecFloats * 4); // this warp's record inside a hand-off buffer
+    const uint32_t dump_a = S.red_a + (uint32_t)(mw * kRecFloats * 4);            // this warp's record inside a hand-off buffer
     bar_sync(BAR_PAIR0 + cw, 64);                     // the partner's K tiles of this chunk are staged
-    unsigned long long xr[8];
-    if (XREG) load_xr(S, d, cw, lane, xr);
+    unsigned long long xr[4];
+    if (XREG) {       // KT == 2: this group owns K tile (g ^ parity of the phase's first tile) of every row group; KT == 1: tile 0
+        const int kt = KT == 2 ? (int)((g ^ c.ring.odd) & 1u) : 0;
+        const int cc = kt * CT + col;
+        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+        if (col < CT && cc < C) {
+            x0 = lds128f(xlane_a + (uint32_t)((kt * CT) << 2));
+            x1 = lds128f(xlane_a + (uint32_t)((kt * CT) << 2) + 512u);
+        }
+        xr[0] = pack2(x0.x, x0.y); xr[1] = pack2(x0.z, x0.w); xr[2] = pack2(x1.x, x1.y); xr[3] = pack2(x1.z, x1.w);
+    }
     mark(pm, p, phase_idx, PROF_PROLOGUE);
     bool first = pm != nullptr;
     int ntile = 0;
-    float pend[kHalf];
-    bool have = false;
+    float pend[kRows];
+    bool have = false, pend_real = false;
     RowIt it;
     it.init(S.misc, ph, d);
     mark(pm, p, phase_idx, PROF_WAIT_FULL);     // schedule computed, about to wait for the first tile
     for (; it.valid(); it.next()) {
         for (int sub = 0; sub < nsub; ++sub) {
-            unsigned long long acc[kHalf];                    // (even-column sum, odd-column sum) per row
+            unsigned long long acc[kRows];                    // (even-column sum, odd-column sum) per row
 #pragma unroll
-            for (int r = 0; r < kHalf; ++r) acc[r] = 0ull;
-            if (XREG) {
-#pragma unroll
-                for (int kt = 0; kt < 2; ++kt) {
-                    if (kt < KT) {
-                        const int ncols = min(CT, C - kt * CT);
-                        const uint32_t stride = (uint32_t)ncols * 2u;
-                        const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (uint32_t)(rh * kHalf) * stride + (col < ncols ? (uint32_t)col << 1 : 0u);
-                        wait_full(p, S, c, 3);
-                        if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
-                        uint4 w[kHalf];
-#pragma unroll
-                        for (int r = 0; r < kHalf; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
-                        if (kt == 0 && have) { flush_group(p, S, c, gq, pend, ss, dump_a, lane); have = false; }
-#pragma unroll
-                        for (int r = 0; r < kHalf; ++r) fma8(w[r], &xr[kt * 4], acc[r]);
-                        release_slot(S, c, lane);
-                        if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
-                    }
-                }
-            } else {
-                int col0 = 0;
-                for (int kt = 0; kt < KT; ++kt, col0 += CT) {
+            for (int r = 0; r < kRows; ++r) acc[r] = 0ull;
+            bool mine_any = false;
+            int col0 = 0;
+#pragma unroll 1
+            for (int kt = 0; kt < KT; ++kt, col0 += CT) {
+                if (c.ring.odd == g) {
                     const int ncols = min(CT, C - col0);
                     const bool ok = col < ncols;                       // lanes past a short tile's last column read column 0 against zeros
                     const uint32_t stride = (uint32_t)ncols * 2u;
-                    const uint32_t xa = ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4);
-                    const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (uint32_t)(rh * kHalf) * stride + (ok ? (uint32_t)col << 1 : 0u);
-                    wait_full(p, S, c, 3);
+                    const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (ok ? (uint32_t)col << 1 : 0u);
+                    if (c.ready) c.ready = false;                      // seen complete by the look-ahead of the previous tile
+                    else wait_full(p, S, c, 3);
                     if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
-                    float4 x0 = lds128f(xa), x1 = lds128f(xa + 512u);
-                    uint4 w[kHalf];
+                    unsigned long long xp[4];
+                    uint4 w[kRows];
+                    if (XREG) {
 #pragma unroll
-                    for (int r = 0; r < kHalf; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
-                    if (!ok) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
-                    if (kt == 0 && have) { flush_group(p, S, c, gq, pend, ss, dump_a, lane); have = false; }
-                    const unsigned long long xp[4] = {pack2(x0.x, x0.y), pack2(x0.z, x0.w), pack2(x1.x, x1.y), pack2(x1.z, x1.w)};
+                        for (int r = 0; r < kRows; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
 #pragma unroll
-                    for (int r = 0; r < kHalf; ++r) fma8(w[r], xp, acc[r]);
-                    release_slot(S, c, lane);
+                        for (int j = 0; j < 4; ++j) xp[j] = xr[j];
+                    } else {
+                        const uint32_t xa = ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4);
+                        float4 x0 = lds128f(xa), x1 = lds128f(xa + 512u);
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
+                        if (!ok) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
+                        xp[0] = pack2(x0.x, x0.y); xp[1] = pack2(x0.z, x0.w); xp[2] = pack2(x1.x, x1.y); xp[3] = pack2(x1.z, x1.w);
+                    }
+                    if (!c.dead) c.ready = peek_tile_after_next(S, c);
+                    if (have) { flush_group(p, S, c, gq, pend, pend_real, ss, dump_a, lane); have = false; }
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) fma8(w[r], xp, acc[r]);
+                    if (lane == 0) mbar_arrive(S.empty_a + c.ring.sl * 8);       // (the FMAs above consumed every lane's loads)
+                    mine_any = true;
                     if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
                 }
+                c.ring.advance();
             }
+            if (have) flush_group(p, S, c, gq, pend, pend_real, ss, dump_a, lane);     // (a row group without a tile of ours in between)
 #pragma unroll
-            for (int r = 0; r < kHalf; ++r) {
+            for (int r = 0; r < kRows; ++r) {
                 float lo, hi;
                 asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[r]));
                 pend[r] = lo + hi;
             }
             have = true;
+            pend_real = mine_any;
         }
     }
-    if (have) flush_group(p, S, c, gq, pend, ss, dump_a, lane);
+    if (have) flush_group(p, S, c, gq, pend, pend_real, ss, dump_a, lane);
     mark(pm, p, phase_idx, PROF_LAST_TILE);
     bar_sync(BAR_PAIR0 + cw, 64);                 // both warps are done reading xs before the next prologue overwrites it
     return pack_state(gq, c.ring);
@@ -776,10 +844,12 @@ __device__ __forceinline__ float wait_flagged1(const DecParams& p, const unsigne
 // prologue merges the splits of a head.
 __device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, unsigned long long state, int layer) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31;
-    Cons c{{0u, 0u}, false};
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1);
+    const unsigned g = (unsigned)(mw >> 3);
+    Cons c{{0u, 0u, 0u}, false, false};
     unsigned gq;
     unpack_state(state, gq, c.ring);
+    unsigned pair = 0;                                // K/V tile pairs of this phase so far: pair i belongs to group i % 2
     const thk_llama_layer L = p.layers[layer];
     const AttSched a = make_att(p);
     const int D = p.head_dim;
@@ -809,8 +879,9 @@ __device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, un
         }
         float m = -INFINITY, lsum = 0.f;
         float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int pos = pa; pos < pb; pos += p.att_tpos) {
+        for (int pos = pa; pos < pb; pos += p.att_tpos, ++pair) {
             const int np = min(p.att_tpos, pb - pos);
+            if ((pair & 1u) != g) { c.ring.advance(); c.ring.advance(); continue; }     // the other group's pair
             // the K tile and the V tile of these positions sit in consecutive slots
             wait_full(p, S, c, 4);
             const float* kt = (const float*)(S.slots + c.ring.sl * kSlotBytes);
@@ -819,11 +890,11 @@ __device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, un
             wait_full(p, S, cv, 5);
             const float* vt = (const float*)(S.slots + cv.ring.sl * kSlotBytes);
             c.dead = c.dead || cv.dead;
-            for (int j0 = mw; j0 < np; j0 += 4 * kMathWarps) {      // 4 positions of this warp per round
+            for (int j0 = cw; j0 < np; j0 += 4 * kGroupWarps) {      // 4 positions of this warp per round
                 float s[4];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const int j = j0 + t * kMathWarps;
+                    const int j = j0 + t * kGroupWarps;
                     s[t] = (act && j < np) ? dot4(q4, *(const float4*)(kt + j * D + (lane << 2))) : 0.f;
                 }
 #pragma unroll
@@ -833,14 +904,14 @@ __device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, un
                 }
                 float mx = -INFINITY;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) { s[t] = (j0 + t * kMathWarps < np) ? s[t] * scale : -INFINITY; mx = fmaxf(mx, s[t]); }
+                for (int t = 0; t < 4; ++t) { s[t] = (j0 + t * kGroupWarps < np) ? s[t] * scale : -INFINITY; mx = fmaxf(mx, s[t]); }
                 const float m_new = fmaxf(m, mx);
                 const float corr = expf(m - m_new);
                 lsum *= corr; o4.x *= corr; o4.y *= corr; o4.z *= corr; o4.w *= corr;
                 m = m_new;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const int j = j0 + t * kMathWarps;
+                    const int j = j0 + t * kGroupWarps;
                     if (j < np) {
                         const float pj = expf(s[t] - m);
                         lsum += pj;
@@ -914,7 +985,7 @@ __device__ __forceinline__ float4 emb_f4(const uint16_t* row, int i) {
 __device__ __noinline__ float prologue_norm(const DecParams& p, int ph, const uint16_t* emb_row, const unsigned long long* fsrc, unsigned epoch,
                                             const float* gain, unsigned long long* xf_out) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw >> 1, rh = mw & 1;
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1), rh = mw >> 3;   // rh: the warp's group
     const PhaseDesc& d = p.ph[ph];
     bool dead = false;
     const int n = d.C;
@@ -965,7 +1036,7 @@ __device__ __noinline__ float prologue_norm(const DecParams& p, int ph, const ui
 // xs <- the FFN hidden vector for W2, from the flagged vector (waits for `epoch`)
 __device__ __noinline__ void prologue_copy(const DecParams& p, int ph, const unsigned long long* fsrc, unsigned epoch) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw >> 1, rh = mw & 1;
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1), rh = mw >> 3;   // rh: the warp's group
     const PhaseDesc& d = p.ph[ph];
     bool dead = false;
     const int n = d.C;
@@ -997,7 +1068,7 @@ __device__ __noinline__ void prologue_copy(const DecParams& p, int ph, const uns
 // records by every CTA costs more than the two grid barriers it removes.)
 __device__ __noinline__ void prologue_att_merge(const DecParams& p, int ph) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw >> 1, rh = mw & 1;
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1), rh = mw >> 3;   // rh: the warp's group
     const PhaseDesc& d = p.ph[ph];
     const AttSched a = make_att(p);
     const int D = p.head_dim, ps = part_stride(p);
@@ -1048,6 +1119,7 @@ __device__ __forceinline__ void prefetch_gain(const float* gain, int n, int ct) 
 }
 
 __device__ void math_main(const DecParams& p, int tok) {
+    const long long t_life = wstat_t0();
     const int ct = (int)threadIdx.x - kMathBase;
     unsigned long long* const pm = (PROF(p) != nullptr && ct == 0) ? PROF(p) + (size_t)blockIdx.x * kProfPhases * 8 : nullptr;
     unsigned long long state = 0ull;      // row groups handed over, ring position
@@ -1060,6 +1132,7 @@ __device__ void math_main(const DecParams& p, int tok) {
         const thk_llama_layer* L = p.layers + (l < p.n_layer ? l : p.n_layer - 1);
         // ---- prologue ----
         const unsigned epoch = p.flag_epoch + (unsigned)l + 1u;          // flagged vectors written in layer l (K_QKV / K_OUT read layer l-1's x)
+        const long long tp0 = wstat_t0();
         if (k == K_QKV || k == K_W13 || k == K_OUT) {
             const float* gain = (k == K_QKV) ? L->attention_norm : (k == K_W13) ? L->ffn_norm : p.norm;
             // step 0: x <- f32(tok_embeddings[token]) (th-llama.cpp:577-585; device-side like :552-575): every CTA converts
@@ -1071,6 +1144,7 @@ __device__ void math_main(const DecParams& p, int tok) {
         } else if (k == K_W2) {
             prologue_copy(p, PH_W2, p.fff, epoch);
         }
+        wstat_add(WS_POLL, tp0);
         // ---- tiles ----
         if (k == K_ATT) {
             mark(pm, p, (unsigned)i, PROF_PROLOGUE);
@@ -1092,6 +1166,7 @@ __device__ void math_main(const DecParams& p, int tok) {
         mark(pm, p, (unsigned)i + 1, PROF_START);
         if (k == K_W2) { ++l; k = (l < p.n_layer) ? K_QKV : K_OUT; } else ++k;
     }
+    wstat_flush(PROF(p), t_life);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1102,6 +1177,7 @@ __device__ void math_main(const DecParams& p, int tok) {
 // __syncwarp / bar.sync order those writes before lane 0's gpu-scope release (cumulativity), and the
 // acquire fence + BAR_ALL make the other CTAs' writes visible to every thread here (read with .cg).
 __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, int lane, bool& dead) {
+    const long long tw0 = wstat_t0();
     __syncwarp();
     if (lane == 0 && !dead && !p.nosync) {
         unsigned* const ctr = p.bar_ctr;
@@ -1115,6 +1191,7 @@ __device__ __forceinline__ void grid_barrier(const DecParams& p, unsigned nbar, 
         asm volatile("fence.acquire.gpu;" ::: "memory");
     }
     dead = __shfl_sync(0xffffffffu, dead ? 1 : 0, 0) != 0;
+    wstat_add(WS_POLL, tw0);
 }
 
 enum EpiKind { EPI_QKV, EPI_WO, EPI_W13, EPI_W2, EPI_OUT };
@@ -1126,9 +1203,9 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
     const PhaseDesc& d = p.ph[ph];
     const int D = p.head_dim, tp_size = kTP ? p.tp_size : 1, tp_rank = kTP ? p.tp_rank : 0, n_ctx = p.n_ctx, n_past = p.n_past;
     const int nsub = d.paired ? 2 : 1;
-    // lane (r, q): row r = lane & 7 of the group (row half r >> 2), chunks 2q and 2q + 1
+    // lane (r, q): row r = lane & 7 of the row group, math warps 4q .. 4q + 3
     const int rr = lane & 7, qq = lane >> 3;
-    const uint32_t my_a = S.red_a + (uint32_t)((((4 * qq) + (rr >> 2)) * kRecFloats + (rr & 3)) * 4);
+    const uint32_t my_a = S.red_a + (uint32_t)(((4 * qq) * kRecFloats + rr) * 4);
     const bool has_resid = (kind == EPI_WO || kind == EPI_W2) && !kTP;
     const bool need_scale = (kind == EPI_QKV || kind == EPI_W13 || kind == EPI_OUT);
     bool have_scale = false;
@@ -1151,17 +1228,23 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
             if (has_resid) {
                 if (row0 + nrows > rbase + 32) {
                     rbase = row0;
+                    const long long t0 = wstat_t0();
                     rval = wait_flagged1(p, rsrc + min(rbase + lane, p.n_embd - 1), repoch, dead);
+                    wstat_add(WS_HANDOFF, t0);
                 }
                 resid = __shfl_sync(0xffffffffu, rval, (row0 - rbase + rr) & 31);
             }
             const unsigned buf = gq & (kDumpBufs - 1), use = gq / kDumpBufs;
             if (!dead) {
                 const uint32_t fb = S.red_full_a + buf * 8;
-                if (!mbar_try_wait(fb, use & 1u)) dead = !mbar_wait_slow(p.status, p.timeout_ns, fb, use & 1u, 7);
+                if (!mbar_try_wait(fb, use & 1u)) {
+                    const long long t0 = wstat_t0();
+                    dead = !mbar_wait_slow(p.status, p.timeout_ns, fb, use & 1u, 7);
+                    wstat_add(WS_RING, t0);
+                }
             }
             const uint32_t src = my_a + buf * (uint32_t)(kRedFloats * 4);
-            float y = lds32f(src) + lds32f(src + 2 * kRecFloats * 4);
+            float y = (lds32f(src) + lds32f(src + kRecFloats * 4)) + (lds32f(src + 2 * kRecFloats * 4) + lds32f(src + 3 * kRecFloats * 4));
             y += __shfl_xor_sync(0xffffffffu, y, 8);
             y += __shfl_xor_sync(0xffffffffu, y, 16);      // every lane: total of row (lane & 7)
             if (need_scale && !have_scale) {
@@ -1169,7 +1252,7 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
                 // shares of sum(v^2); added in warp order: deterministic.
                 float tot = 0.f;
 #pragma unroll
-                for (int w = 0; w < kMathWarps; ++w) tot += lds32f(S.red_a + (buf * kRedFloats + w * kRecFloats + kHalf) * 4u);
+                for (int w = 0; w < kMathWarps; ++w) tot += lds32f(S.red_a + (buf * kRedFloats + w * kRecFloats + kRows) * 4u);
                 scale = 1.0f / sqrtf(tot / (float)d.C + 1e-6f);
                 have_scale = true;
             }
@@ -1219,6 +1302,7 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
 
 template <bool kTP>
 __device__ void epi_main(const DecParams& p, const Smem& S) {
+    const long long t_life = wstat_t0();
     const int lane = (int)threadIdx.x & 31;
     EpiState es{0.f, 0.f, -1};
     bool dead = false;
@@ -1306,6 +1390,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
         }
     }
     if (PROF(p) && lane == 0) prof_mark(PROF(p), 5u * (unsigned)p.n_layer + 1u, PROF_START);
+    wstat_flush(PROF(p), t_life);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1373,14 +1458,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNumSlots; ++i) {
             mbar_init(S.full_a + i * 8, 1);
-            mbar_init(S.empty_a + i * 8, kMathWarps);
+            mbar_init(S.empty_a + i * 8, kGroupWarps);          // a tile is consumed by one group
         }
         for (int i = 0; i < kDumpBufs; ++i) {
-            mbar_init(S.red_full_a + i * 8, kMathWarps);
+            mbar_init(S.red_full_a + i * 8, kMathWarps * kRecArrivals);
             mbar_init(S.red_free_a + i * 8, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (blockIdx.x == 0) *p.bar_next = 0u;   // arm the next launch's barrier counter
+    }
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&p);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&S.misc->prm);
+        for (int i = threadIdx.x; i < (int)(sizeof(DecParams) / 4); i += kThreads) dst[i] = src[i];
+        if (PROF(p) && threadIdx.x < (kMathWarps + kSvcWarps) * 4) (&S.misc->wstat[0][0])[threadIdx.x] = 0ull;
     }
     // A token id outside the vocabulary (th-llama.cpp:606 asserts) is the same on every CTA (and every rank): the whole
     // grid leaves before any phase starts, nothing waits on anything, and the host reads THK_E_INVALID from the status word.
@@ -1388,15 +1479,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
         if (threadIdx.x == 0 && blockIdx.x == 0) raise_abort(p, 0x300u, (unsigned)tok, 0u);
         return;
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 69) {            // (lanes of the reducer warp)
-        const int ph = (int)threadIdx.x - 64;
+    if (threadIdx.x >= kSvcBase + 64 && threadIdx.x < kSvcBase + 69) {            // (lanes of the reducer warp)
+        const int ph = (int)threadIdx.x - (kSvcBase + 64);
         RowIt::share(p.ph[ph], gridDim.x, blockIdx.x, S.misc->range[ph][0], S.misc->range[ph][1]);
     }
     __syncthreads();
-    if (threadIdx.x < 32) producer_main(p, S);
-    else if (threadIdx.x < 64) epi_main<kTP>(p, S);
-    else if (threadIdx.x < kMathBase) { if (kTP) reducer_main(p, tok); }
-    else math_main(p, tok);
+    const int sw = ((int)threadIdx.x - kSvcBase) >> 5;             // service warp index (meaningless for math threads)
+    if ((int)threadIdx.x >= kMathBase && (int)threadIdx.x < kMathBase + kMathThreads) math_main(S.misc->prm, tok);   // (the shared-memory copy of the parameters)
+    else if (sw == 0) producer_main(p, S);
+    else if (sw == 1) epi_main<kTP>(p, S);
+    else if (kTP) reducer_main(p, tok);
 }
 
 size_t decode_smem_bytes(int max_vec) {
@@ -1619,14 +1711,14 @@ extern "C" int thk_decoder_profile(thk_decoder* d, int enable, unsigned long lon
 #endif
     THK_ENTER(d->ctx);
     if (enable && !d->d_prof) {
-        const size_t nprof = (size_t)d->grid * (kProfPhases * 8 + 4 + 2 * kProfTiles);
+        const size_t nprof = (size_t)d->grid * (kProfPhases * 8 + 4 + 2 * kProfTiles + kProfWarps * 4);
         THK_CUDA(cudaMalloc(&d->d_prof, nprof * sizeof(unsigned long long)));
         THK_CUDA(cudaMemset(d->d_prof, 0, nprof * sizeof(unsigned long long)));
     }
     d->p.prof = enable ? d->d_prof : nullptr;
     if (host_out && n > 0 && d->d_prof) {
         THK_CUDA(cudaStreamSynchronize(d->ctx->stream));
-        const size_t nprof = (size_t)d->grid * (kProfPhases * 8 + 4 + 2 * kProfTiles);
+        const size_t nprof = (size_t)d->grid * (kProfPhases * 8 + 4 + 2 * kProfTiles + kProfWarps * 4);
         THK_CUDA(cudaMemcpy(host_out, d->d_prof, sizeof(unsigned long long) * ((size_t)n > nprof ? nprof : (size_t)n), cudaMemcpyDeviceToHost));
     }
     return THK_OK;

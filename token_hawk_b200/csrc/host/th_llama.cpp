@@ -444,6 +444,32 @@ static bool eval_batch_opgraph(WGPUDevice device, WGPUQueue queue, std::shared_p
     return thk_gemm_check(device) == THK_OK;
 }
 
+// One authoritative KV row per position: before a path evaluates at n_past, the rows [0, n_past) it has not written
+// itself are copied over from the other path's layout; after it wrote [n_past, n_past + T) the other layout is stale
+// from n_past on.  (Tensor parallel models only run the fused path.)
+static bool kv_sync(std::shared_ptr<LlamaModel> m, bool want_hpd, int n_past, int T) {
+    if (m->tp_size == 1) {
+        int32_t& have = want_hpd ? m->kvValidHpd : m->kvValidPhd;
+        const int32_t other = want_hpd ? m->kvValidPhd : m->kvValidHpd;
+        if (have < n_past) {
+            if (other < n_past) { fprintf(stderr, "th_eval_gpu: n_past %d but only %d positions were evaluated\n", n_past, std::max(have, other)); return false; }
+            const int64_t H = m->n_head, D = m->n_embd / m->n_head;
+            for (auto& l : m->layers) {
+                const int rc = want_hpd
+                    ? (thk_kv_to_hpd(m->device, (const float*)l.key_cache.gpu, (float*)l.key_cache_hpd.gpu, have, n_past - have, m->n_ctx, H, D) ||
+                       thk_kv_to_hpd(m->device, (const float*)l.value_cache.gpu, (float*)l.value_cache_hpd.gpu, have, n_past - have, m->n_ctx, H, D))
+                    : (thk_kv_from_hpd(m->device, (const float*)l.key_cache_hpd.gpu, (float*)l.key_cache.gpu, have, n_past - have, m->n_ctx, H, D) ||
+                       thk_kv_from_hpd(m->device, (const float*)l.value_cache_hpd.gpu, (float*)l.value_cache.gpu, have, n_past - have, m->n_ctx, H, D));
+                if (rc) { fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error()); return false; }
+            }
+        }
+        have = n_past + T;
+        int32_t& stale = want_hpd ? m->kvValidPhd : m->kvValidHpd;
+        stale = std::min<int32_t>(stale, n_past);
+    }
+    return true;
+}
+
 tk_llama_token th_eval_gpu(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens,
                            int n_tokens, int n_past) {
     if (th_eval_gpu_launch(device, queue, m, tokens, n_tokens, n_past) != 0) return -1;
@@ -466,6 +492,8 @@ int th_eval_gpu_launch(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Llama
         // new KV rows are handed to the fused decoder's cache layout
         for (int t0 = 0; t0 < n_tokens; t0 += m->n_batch) {
             const int T = std::min<int>(m->n_batch, n_tokens - t0);
+            if (!kv_sync(m, false, n_past + t0, T)) return -1;
+            if (m->kvValidHpd >= n_past + t0) m->kvValidHpd = n_past + t0 + T;      // eval_batch_opgraph hands its rows to the fused layout too
             if (!eval_batch_opgraph(device, queue, m, tokens + t0, T, n_past + t0)) { fprintf(stderr, "th_eval_gpu: batched prefill failed\n"); return -1; }
         }
         m->gpuLaunches = g_launch_count - launches0;
@@ -476,6 +504,7 @@ int th_eval_gpu_launch(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Llama
         if (tok < 0 || tok >= m->n_vocab) { fprintf(stderr, "th_eval_gpu: token %d outside the vocabulary\n", tok); return -1; }
         if (m->evalPath == EvalPath_Fused) {
             if (!m->decoder) { fprintf(stderr, "th_eval_gpu: fused decoder missing\n"); return -1; }
+            if (!kv_sync(m, true, n_past + i, 1)) return -1;
             if (thk_upload(queue, m->d_token, 0, &tok, sizeof(int32_t))) { fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error()); return -1; }
             if (thk_decoder_step(m->decoder, m->d_token, n_past + i, (float*)m->out.gpu, m->d_next, nullptr)) {
                 fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error());
@@ -483,6 +512,7 @@ int th_eval_gpu_launch(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Llama
             }
             fused_launches += 1;
         } else {
+            if (!kv_sync(m, false, n_past + i, 1)) return -1;
             if (!eval_one_opgraph(device, queue, m, tok, n_past + i)) { fprintf(stderr, "th_eval_gpu: op graph failed\n"); return -1; }
         }
     }

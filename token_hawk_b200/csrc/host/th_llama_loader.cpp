@@ -352,6 +352,8 @@ bool fill_kv_synthetic(std::shared_ptr<LlamaModel> m, uint64_t seed, int n_posit
         if (thk_transpose(m->device, (const float*)L.key_cache_hpd.gpu, (float*)L.key_cache.gpu, Hl, m->n_ctx, D, 1, nullptr)) return false;
         if (thk_transpose(m->device, (const float*)L.value_cache_hpd.gpu, (float*)L.value_cache.gpu, Hl, m->n_ctx, D, 1, nullptr)) return false;
     }
+    m->kvValidPhd = m->tp_size == 1 ? n_positions : 0;
+    m->kvValidHpd = n_positions;
     return thk_sync(m->device) == THK_OK;
 }
 

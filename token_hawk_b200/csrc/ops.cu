@@ -453,3 +453,22 @@ extern "C" int thk_kv_to_hpd(thk_ctx* ctx, const float* src_phd, float* dst_hpd,
     THK_LAUNCH_CHECK();
     return THK_OK;
 }
+// the inverse hand-over: rows [pos0, pos0+npos) of the fused decoder's [head][n_ctx][dim] cache back into the op graph's
+// [pos][head][dim] cache, so that a batched pass or the op graph can continue a context the fused kernel extended
+__global__ void kv_from_hpd_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t pos0, int64_t npos, int64_t n_ctx,
+                                   int64_t H, int64_t D) {
+    const int64_t total = npos * H * D;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = i % D, h = (i / D) % H, pz = i / (D * H);
+        dst[((pos0 + pz) * H + h) * D + d] = src[(h * n_ctx + pos0 + pz) * D + d];
+    }
+}
+extern "C" int thk_kv_from_hpd(thk_ctx* ctx, const float* src_hpd, float* dst_phd, int64_t pos0, int64_t npos, int64_t n_ctx, int64_t H,
+                               int64_t D) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx && src_hpd && dst_phd, "thk_kv_from_hpd: null argument");
+    THK_CHECK_ARG(pos0 >= 0 && npos > 0 && pos0 + npos <= n_ctx && H > 0 && D > 0, "thk_kv_from_hpd: bad range");
+    kv_from_hpd_kernel<<<ew_blocks(ctx, npos * H * D), 256, 0, ctx->stream>>>(src_hpd, dst_phd, pos0, npos, n_ctx, H, D);
+    THK_LAUNCH_CHECK();
+    return THK_OK;
+}

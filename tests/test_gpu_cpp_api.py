@@ -15,7 +15,8 @@ def build_cpp_test():
     lib = os.path.join(ROOT, "token_hawk_b200", "lib")
     exe = os.path.join(lib, "th_api_test")
     src = os.path.join(ROOT, "tests", "cpp", "th_api_test.cpp")
-    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+    deps = [src, os.path.join(lib, "libth_b200.so")] + [os.path.join(ROOT, "include", "th", f) for f in os.listdir(os.path.join(ROOT, "include", "th"))]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):   # headers change the struct layouts
         subprocess.check_call([build.CXX, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
                                "-L" + lib, "-lth_b200", "-lthk_sm100a", "-Wl,-rpath," + lib])
     return exe

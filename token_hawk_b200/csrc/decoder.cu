@@ -38,27 +38,29 @@
 namespace {
 
 constexpr int kSlotBytes = 32 * 1024;
-constexpr int kNumSlots = 5;                          // two tiles are being consumed at any time (one per warp group), three are in flight
-constexpr int kChunks = 8;                            // 256-column chunks per tile
-constexpr int kGroupWarps = 8;                        // warps per consumer group: one per chunk
-constexpr int kGroups = 2;                            // consumer groups; tile t of the CTA's stream belongs to group t % 2
-constexpr int kMathWarps = kGroups * kGroupWarps;     // (group, chunk)
-constexpr int kMathThreads = kMathWarps * 32;
-constexpr int kSvcWarps = 3;                          // producer, epilogue, reducer
-#ifdef THK_SVC_FIRST                                  // (A/B variant: service warps on the lowest warp ids)
-constexpr int kMathBase = kSvcWarps * 32, kSvcBase = 0;
+#ifdef THK_SLOTS
+constexpr int kNumSlots = THK_SLOTS;
 #else
-constexpr int kMathBase = 0;                          // math warps 0-15; the service warps take the HIGHEST warp ids: the warp scheduler
-constexpr int kSvcBase = kMathThreads;                // prefers high warp ids, and producer / epilogue must never wait behind four busy math warps
+constexpr int kNumSlots = 4;                          // measured (r2, v7): 4 slots 2.633, 5 slots 2.638 ms/token -- equal; 4 leaves 40 KB of L1
 #endif
-constexpr int kThreads = kMathThreads + kSvcWarps * 32;   // 608 threads: 96 registers each (warps are allocated in fours), no setmaxnreg
+constexpr int kChunks = 8;                            // 256-column chunks per tile
+constexpr int kMathWarps = 8;                         // one per chunk
+constexpr int kMathThreads = kMathWarps * 32;
+constexpr int kSvcWarps = 4;                          // producer, epilogue, reducer (tensor parallel), one idle warp: 12 warps = 384 threads
+constexpr int kMathBase = 0;                          // math warps 0-7; the service warps take the highest warp ids
+constexpr int kSvcBase = kMathThreads;
+constexpr int kThreads = kMathThreads + kSvcWarps * 32;   // 384 threads = 3 warpgroups: two of math warps, one of service warps
+// A 12-warp CTA launches with 168 registers per thread; the service warpgroup hands registers to the two math warpgroups
+// (setmaxnreg: 72 + 2 * 216 <= 512 per sub-partition lane).  Any ABI call in the kernel makes ptxas ignore the per-branch
+// budgets, so the kernel has none (the timeline profiler is only compiled into lib_prof).
+constexpr int kServiceRegs = 72, kMathRegs = 216;
 constexpr int kRows = 8;                              // rows per row group (= per tile)
 constexpr int kMaxTilePos = 128;                      // attention: positions per tile cap
 constexpr int kMaxHeadDim = 128;
 constexpr int kMaxSplit = 8;                          // attention: KV splits per head cap
 constexpr int kDumpBufs = 8;                          // row-group hand-off ring between the math warps and the epilogue warp
 constexpr int kMaxOwn = 4;                            // tensor parallel: residual elements per reducer lane (n_embd <= 128 * grid)
-enum NamedBarrier { BAR_ALL = 1, BAR_MATH = 2, BAR_PRE = 3, BAR_PAIR0 = 4 };   // BAR_PAIR0 + chunk: the two warps of a chunk
+enum NamedBarrier { BAR_ALL = 1, BAR_MATH = 2, BAR_PRE = 3 };
 
 // Host-computed tile schedule of one matvec phase
 struct PhaseDesc {
@@ -249,10 +251,12 @@ __device__ __forceinline__ void raise_abort(const DecParams& p, unsigned code, u
     if (atomicCAS(p.status, 0u, code) == 0u) { p.status[1] = a; p.status[2] = b; p.status[3] = blockIdx.x; }
 }
 
-// Slow path of every mbarrier wait: bounded by %globaltimer, out of line (one copy; the hot loops stay small).  Returns
-// false when the watchdog fired or another CTA aborted; the caller then walks the rest of its (static) schedule without
-// waiting and without issuing copies, so the kernel terminates and the host sees THK_E_TIMEOUT instead of a wedged GPU.
-__device__ __noinline__ bool mbar_wait_slow(unsigned* status, unsigned long long timeout_ns, uint32_t bar, uint32_t parity, unsigned tag) {
+// Slow path of every mbarrier wait: bounded by %globaltimer.  Returns false when the watchdog fired or another CTA
+// aborted; the caller then walks the rest of its (static) schedule without waiting and without issuing copies, so the
+// kernel terminates and the host sees THK_E_TIMEOUT instead of a wedged GPU.  Inlined: a CALL inside the tile loop forces
+// everything that is live across it (accumulators, activations) through the few callee-saved registers of the ABI --
+// ptxas then keeps the accumulators in local memory.
+__device__ __forceinline__ bool mbar_wait_slow(unsigned* status, unsigned long long timeout_ns, uint32_t bar, uint32_t parity, unsigned tag) {
     if (ld_volatile_u32(status) != 0) return false;      // an abort is sticky: after it every wait gives up at once
     const unsigned long long t0 = gtimer();
     unsigned it = 0;
@@ -267,8 +271,8 @@ __device__ __noinline__ bool mbar_wait_slow(unsigned* status, unsigned long long
     }
     return true;
 }
-// watchdog step of the global-memory polls (out of line); returns true when the poller must give up
-__device__ __noinline__ bool poll_watchdog(unsigned* status, unsigned long long timeout_ns, unsigned long long& t0, unsigned code, unsigned a, unsigned b) {
+// watchdog step of the global-memory polls; returns true when the poller must give up
+__device__ __forceinline__ bool poll_watchdog(unsigned* status, unsigned long long timeout_ns, unsigned long long& t0, unsigned code, unsigned a, unsigned b) {
     if (ld_volatile_u32(status) != 0) return true;
     if (t0 == 0) { t0 = gtimer(); return false; }
     if (gtimer() - t0 > timeout_ns) {
@@ -288,18 +292,15 @@ struct SmemMisc {
     unsigned long long red_free[kDumpBufs];   // ... and consumed by the epilogue warp
     float2 rope[kMaxHeadDim / 2];       // (cos, sin) of n_past * theta_i for this token
     int range[5][2];                    // this CTA's row range [r, r_end) of every matvec phase (computed once per launch)
-    DecParams prm;                      // the kernel parameters for the out-of-line phase functions of the math warps (a reference to the
-                                        // __grid_constant__ parameter would turn every field access into a global load)
+    int niter[5];                       // ... and its number of (row group, segment-of-a-pair) iterations: all a math warp needs to know
     unsigned long long wstat[kMathWarps + kSvcWarps][4];   // -DTHK_PROFILE: cycles a warp spent waiting, see WaitSlot
 };
 constexpr int kMiscBytes = 2048;
 static_assert(sizeof(SmemMisc) <= kMiscBytes, "SmemMisc too large");
-static_assert(sizeof(DecParams) % 4 == 0, "DecParams is copied word by word");
 constexpr int kRecFloats = kRows + 1;                          // per warp: 8 row sums + its share of sum(v^2) of the phase input
-constexpr int kRecArrivals = kRows + 1;                        // every lane that writes a record word arrives itself (no __syncwarp)
 constexpr int kRedFloats = kMathWarps * kRecFloats;            // one row-group hand-off record
 constexpr int kAttScratchOff = kDumpBufs * kRedFloats;         // attention scratch (floats) behind the hand-off ring
-constexpr int kRedBytes = 14 * 1024;                           // ring (4.5 KB) + attention scratch (<= 9.2 KB)
+constexpr int kRedBytes = 8 * 1024;                            // ring (2.3 KB) + attention scratch (<= 5.1 KB)
 static_assert(kAttScratchOff * 4 + (kMathWarps * kMaxHeadDim + 2 * kMathWarps + 2 * kMaxHeadDim) * 4 <= kRedBytes, "attention scratch does not fit");
 constexpr int kXsOffset = kNumSlots * kSlotBytes + kMiscBytes + kRedBytes;
 
@@ -366,25 +367,16 @@ __device__ __forceinline__ void wstat_flush(unsigned long long*, long long) {}
 
 // ring position shared by producer and consumers (kept incrementally: no modulo per tile)
 struct Ring {
-    uint32_t sl, par, odd;      // slot, phase parity of its barriers, parity of the tile counter (consumer group that owns the tile)
-    __device__ __forceinline__ void advance() { odd ^= 1u; if (++sl == kNumSlots) { sl = 0; par ^= 1u; } }
+    uint32_t sl, par;           // slot, phase parity of its barriers
+    __device__ __forceinline__ void advance() { if (++sl == kNumSlots) { sl = 0; par ^= 1u; } }
 };
 
 // per-thread consumer state
 struct Cons {
     Ring ring;
     bool dead;            // watchdog fired somewhere: stop waiting, keep walking the schedule
-    bool ready;           // the group's NEXT tile was already seen complete by the look-ahead test_wait
 };
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {      // non-blocking
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
+// Wait for the tile in the current ring slot (the math warps consume the tiles in order, so a parity wait cannot alias).
 __device__ __forceinline__ void wait_full(const DecParams& p, const Smem& S, Cons& c, unsigned tag) {
     if (c.dead) return;
     const uint32_t bar = S.full_a + c.ring.sl * 8;
@@ -399,15 +391,6 @@ __device__ __forceinline__ void release_slot(const Smem& S, Cons& c, int lane) {
     if (lane == 0) mbar_arrive(S.empty_a + c.ring.sl * 8);
     c.ring.advance();
 }
-// Look-ahead for this group's next tile (two tiles on): a NON-blocking test, issued right after the current tile's
-// shared loads so that its ~100+ cycles of latency hide behind the tile's math.  (The blocking try_wait costs 135-400
-// cycles per tile on the consumer's serial path even when the tile landed long ago: ncu, profiles/v5a.)
-__device__ __forceinline__ bool peek_tile_after_next(const Smem& S, const Cons& c) {
-    uint32_t sl = c.ring.sl + 2u, par = c.ring.par;
-    if (sl >= (uint32_t)kNumSlots) { sl -= (uint32_t)kNumSlots; par ^= 1u; }
-    return mbar_test_wait(S.full_a + sl * 8, par);
-}
-
 // ------------------------------------------------------------------------------------------
 // this CTA's share of a phase: contiguous (even-aligned) row range of the concatenated segments,
 // walked in groups of up to kRows rows; the last group of a range (or of a segment) may be short.
@@ -570,7 +553,7 @@ __device__ __forceinline__ int phase_of(int k) { return k == K_QKV ? PH_QKV : k 
 
 __device__ void producer_main(const DecParams& p, const Smem& S) {
     const long long t0 = clock64();
-    Prod c{{0u, 0u, 0u}, false, 0u, 0, l2_evict_first_policy()};
+    Prod c{{0u, 0u}, false, 0u, 0, l2_evict_first_policy()};
     const int nsteps = 5 * p.n_layer + 1;
     int l = 0, k = K_QKV;                                 // same step order as the consumers
     for (int i = 0; i < nsteps; ++i) {
@@ -623,32 +606,24 @@ __device__ __forceinline__ void fma8(const uint4& w, const unsigned long long* x
 // Hand the eight row sums of a finished row group to the epilogue warp.  A transposing shuffle reduction (4 + 2 + 1
 // exchanges halve the rows a lane holds while doubling the lanes summed, then 2 plain steps) leaves the warp total of row
 // (lane >> 2) & 7 in every lane; 8 floats per warp go into a ring of kDumpBufs hand-off records, so the math warps can run
-// kDumpBufs row groups ahead of the epilogue warp.  Fixed order of additions: deterministic.  `real` == false: this warp
-// owned no tile of the row group (its group's turn fell on other row groups): zeros, no reduction.  Every lane that
-// writes a word of the record arrives on the record's barrier itself, so no __syncwarp is needed.
-// Called one tile AFTER the group's last tile, between that tile's shared loads and its math, so the shuffle latency
-// overlaps the load latency.
-__device__ __forceinline__ void flush_group(const DecParams& p, const Smem& S, Cons& c, unsigned& gq, float (&v)[kRows], bool real, float ss,
+// kDumpBufs row groups ahead of the epilogue warp.  Fixed order of additions: deterministic.
+__device__ __forceinline__ void flush_group(const DecParams& p, const Smem& S, Cons& c, unsigned& gq, float (&v)[kRows], float ss,
                                             uint32_t dump_a, int lane) {
-    if (real) {
-        const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
+    const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float recv = __shfl_xor_sync(0xffffffffu, u4 ? v[r] : v[r + 4], 16);
-            v[r] = (u4 ? v[r + 4] : v[r]) + recv;
-        }
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const float recv = __shfl_xor_sync(0xffffffffu, u3 ? v[r] : v[r + 2], 8);
-            v[r] = (u3 ? v[r + 2] : v[r]) + recv;
-        }
-        const float recv = __shfl_xor_sync(0xffffffffu, u2 ? v[0] : v[1], 4);
-        v[0] = (u2 ? v[1] : v[0]) + recv;
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-    } else {
-        v[0] = 0.f;
+    for (int r = 0; r < 4; ++r) {
+        const float recv = __shfl_xor_sync(0xffffffffu, u4 ? v[r] : v[r + 4], 16);
+        v[r] = (u4 ? v[r + 4] : v[r]) + recv;
     }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const float recv = __shfl_xor_sync(0xffffffffu, u3 ? v[r] : v[r + 2], 8);
+        v[r] = (u3 ? v[r + 2] : v[r]) + recv;
+    }
+    const float recv = __shfl_xor_sync(0xffffffffu, u2 ? v[0] : v[1], 4);
+    v[0] = (u2 ? v[1] : v[0]) + recv;
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
     const unsigned buf = gq & (kDumpBufs - 1), use = gq / kDumpBufs;
     if (use > 0 && !c.dead) {
         const uint32_t fb = S.red_free_a + buf * 8;
@@ -658,124 +633,134 @@ __device__ __forceinline__ void flush_group(const DecParams& p, const Smem& S, C
             wstat_add(WS_HANDOFF, t0);
         }
     }
-    const uint32_t rb = S.red_full_a + buf * 8;
-    if ((lane & 3) == 0) { sts32f(dump_a + (buf * kRedFloats + (unsigned)((lane >> 2) & 7)) * 4u, v[0]); mbar_arrive(rb); }
-    if (lane == 1) { sts32f(dump_a + (buf * kRedFloats + kRows) * 4u, ss); mbar_arrive(rb); }      // this warp's share of sum(v^2) (norm phases)
+    if ((lane & 3) == 0) sts32f(dump_a + (buf * kRedFloats + (unsigned)((lane >> 2) & 7)) * 4u, v[0]);
+    if (lane == 1) sts32f(dump_a + (buf * kRedFloats + kRows) * 4u, ss);          // this warp's share of sum(v^2) (norm phases)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(S.red_full_a + buf * 8);       // ONE arrival per warp: several lanes arriving on one mbarrier in
+                                                              // the same instruction are not counted per lane (measured: hangs / faults)
     ++gq;
 }
 
 // consumer state carried from phase to phase: row groups handed over so far and the ring position
 __device__ __forceinline__ unsigned long long pack_state(unsigned gq, const Ring& r) {
-    return ((unsigned long long)(r.sl | (r.par << 8) | (r.odd << 16)) << 32) | gq;
+    return ((unsigned long long)(r.sl | (r.par << 8)) << 32) | gq;
 }
 __device__ __forceinline__ void unpack_state(unsigned long long st, unsigned& gq, Ring& r) {
     gq = (unsigned)st;
     r.sl = (unsigned)(st >> 32) & 0xffu;
     r.par = (unsigned)(st >> 40) & 1u;
-    r.odd = (unsigned)(st >> 48) & 1u;
 }
 
-// Stream this CTA's tiles of one matvec phase.  The 16 math warps form two groups of 8; tile t of the CTA's tile stream
-// (all phases, counted from kernel start) is consumed by group t % 2 ALONE -- so two tiles are in progress at any time and
-// a tile's serial chain (wait, shared loads, convert, FMA, release, row-group reduction) of one group hides behind the
-// other group's.  Within its tile a warp owns one 256-column chunk of all 8 rows (rows past a short group's end hold
-// stale bytes; their sums are never read): ten (XREG: eight) 128-bit shared loads by shared-window address, exact
-// f16 -> f32 conversion, packed FFMA2.  Every warp hands its partial row sums -- the K tiles its group owned -- to the
-// epilogue warp once per row group (`gq` counts them since kernel start; hand-off record = gq % kDumpBufs).
-// XREG: the phase has <= 2 K tiles, so a group owns the same K tile of every row group and this lane's 8 activations of
-// that tile (packed for FFMA2; zero for columns past the end) stay in registers; else they are re-read from xs.
-// Out of line on purpose: the function gets its own register allocation (19 warps leave 96 registers per thread), so
-// phase-level state of the caller is parked across the call instead of spilling inside the tile loop.
+// one tile's weights of this lane: 8 rows x 8 columns of f16
+struct TileW { uint4 w[kRows]; };
+__device__ __forceinline__ void tile_ldw(uint32_t wa, uint32_t stride, TileW& t) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) t.w[r] = lds128(wa + (uint32_t)r * stride);
+}
+__device__ __forceinline__ void xs_ld(uint32_t xa, bool ok, unsigned long long (&xp)[4]) {
+    float4 x0 = lds128f(xa), x1 = lds128f(xa + 512u);
+    if (!ok) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
+    xp[0] = pack2(x0.x, x0.y); xp[1] = pack2(x0.z, x0.w); xp[2] = pack2(x1.x, x1.y); xp[3] = pack2(x1.z, x1.w);
+}
+
+// Stream this CTA's tiles of one matvec phase.  Per tile a warp owns one 256-column chunk of all 8 rows (rows past a
+// short group's end hold stale bytes; their sums are never read): eight 128-bit shared loads by shared-window address,
+// exact f16 -> f32 conversion, packed FFMA2 against its lane's 8 activations of that chunk.
+//   * The serial chain of a tile -- wait, shared loads, convert, FMA, release -- is what bounds a CTA's tile rate, not any
+//     pipe (ncu: issue slots 34 % busy, every pipe < 25 %), so everything that is not math is kept off it.
+//   * XREG: the phase has <= 2 K tiles (every 4096-column matrix): this lane's activations (packed for FFMA2; zero for
+//     columns past the end) stay in registers for the whole phase; else they are re-read from xs with the weights.
+//   (A non-blocking look-ahead on the next tile's barrier -- mbarrier.test_wait issued under the math -- was measured and
+//   dropped: 2.67 -> 2.64 ms/token WITHOUT it.)
+// The warp hands its row sums to the epilogue warp once per row group (`gq` counts them since kernel start).
+// (Everything on the math warps' path is inlined: an out-of-line phase function may only use the ABI's scratch registers
+// freely, and ptxas then kept half of the accumulators in local memory; the math warpgroups get their registers from
+// setmaxnreg instead.)
 template <bool XREG>
-__device__ __noinline__ unsigned long long math_mat_phase(const DecParams& p, int ph, unsigned long long state, float ss, unsigned phase_idx) {
+__device__ __forceinline__ unsigned long long math_mat_phase(const DecParams& p, int ph, unsigned long long state, float ss, unsigned phase_idx) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1);
-    const unsigned g = (unsigned)(mw >> 3);
+    const int ct = (int)threadIdx.x - kMathBase, cw = ct >> 5, lane = ct & 31;
     unsigned long long* const pm = (PROF(p) != nullptr && ct == 0) ? PROF(p) + (size_t)blockIdx.x * kProfPhases * 8 : nullptr;
-    Cons c{{0u, 0u, 0u}, false, false};
+    Cons c{{0u, 0u}, false};
     unsigned gq;
     unpack_state(state, gq, c.ring);
     const PhaseDesc& d = p.ph[ph];
-    const int C = d.C, KT = d.KT, CT = d.CT, nsub = d.paired ? 2 : 1;
+    const int C = d.C, KT = d.KT, CT = d.CT;
+    const int n_iters = S.misc->niter[ph];            // (row group, segment-of-a-pair) iterations of this CTA: the rows themselves do not matter here
     const int col = (cw << 8) + (lane << 3);                                  // this lane's first column inside a tile
     const uint32_t xlane_a = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);   // + col0 * 4: first float4; second 512 B on
-    const uint32_t dump_a = S.red_a + (uint32_t)(mw * kRecFloats * 4);            // this warp's record inside a hand-off buffer
-    bar_sync(BAR_PAIR0 + cw, 64);                     // the partner's K tiles of this chunk are staged
-    unsigned long long xr[4];
-    if (XREG) {       // KT == 2: this group owns K tile (g ^ parity of the phase's first tile) of every row group; KT == 1: tile 0
-        const int kt = KT == 2 ? (int)((g ^ c.ring.odd) & 1u) : 0;
-        const int cc = kt * CT + col;
-        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-        if (col < CT && cc < C) {
-            x0 = lds128f(xlane_a + (uint32_t)((kt * CT) << 2));
-            x1 = lds128f(xlane_a + (uint32_t)((kt * CT) << 2) + 512u);
+    const uint32_t dump_a = S.red_a + (uint32_t)(cw * kRecFloats * 4);            // this warp's record inside a hand-off buffer
+    unsigned long long xr[2][4];
+    if (XREG) {
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+            const bool ok = kt < KT && col < CT && kt * CT + col < C;
+            xs_ld(ok ? xlane_a + (uint32_t)((kt * CT) << 2) : S.xs_a + ((uint32_t)lane << 4), ok, xr[kt]);   // (never address past xs)
         }
-        xr[0] = pack2(x0.x, x0.y); xr[1] = pack2(x0.z, x0.w); xr[2] = pack2(x1.x, x1.y); xr[3] = pack2(x1.z, x1.w);
     }
     mark(pm, p, phase_idx, PROF_PROLOGUE);
     bool first = pm != nullptr;
     int ntile = 0;
-    float pend[kRows];
-    bool have = false, pend_real = false;
-    RowIt it;
-    it.init(S.misc, ph, d);
     mark(pm, p, phase_idx, PROF_WAIT_FULL);     // schedule computed, about to wait for the first tile
-    for (; it.valid(); it.next()) {
-        for (int sub = 0; sub < nsub; ++sub) {
-            unsigned long long acc[kRows];                    // (even-column sum, odd-column sum) per row
+#pragma unroll 1
+    for (int it = 0; it < n_iters; ++it) {
+        unsigned long long acc[kRows];                    // (even-column sum, odd-column sum) per row
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) acc[r] = 0ull;
-            bool mine_any = false;
+        for (int r = 0; r < kRows; ++r) acc[r] = 0ull;
+        if (XREG) {
+            // <= 2 K tiles, activations in registers: straight-line code, no column bookkeeping
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                if (kt < KT) {
+                    const int ncols = min(CT, C - kt * CT);
+                    const uint32_t stride = (uint32_t)ncols * 2u;
+                    const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (col < ncols ? (uint32_t)col << 1 : 0u);
+                    wait_full(p, S, c, 3);
+                    if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
+                    const uint32_t eb = S.empty_a + c.ring.sl * 8;
+                    c.ring.advance();
+                    TileW t;
+                    tile_ldw(wa, stride, t);
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) fma8(t.w[r], xr[kt], acc[r]);
+                    __syncwarp();                                 // every lane has read the tile (lanes may have diverged at the waits)
+                    if (lane == 0) mbar_arrive(eb);
+                    if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
+                }
+            }
+        } else {
             int col0 = 0;
 #pragma unroll 1
             for (int kt = 0; kt < KT; ++kt, col0 += CT) {
-                if (c.ring.odd == g) {
-                    const int ncols = min(CT, C - col0);
-                    const bool ok = col < ncols;                       // lanes past a short tile's last column read column 0 against zeros
-                    const uint32_t stride = (uint32_t)ncols * 2u;
-                    const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (ok ? (uint32_t)col << 1 : 0u);
-                    if (c.ready) c.ready = false;                      // seen complete by the look-ahead of the previous tile
-                    else wait_full(p, S, c, 3);
-                    if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
-                    unsigned long long xp[4];
-                    uint4 w[kRows];
-                    if (XREG) {
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) xp[j] = xr[j];
-                    } else {
-                        const uint32_t xa = ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4);
-                        float4 x0 = lds128f(xa), x1 = lds128f(xa + 512u);
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) w[r] = lds128(wa + (uint32_t)r * stride);
-                        if (!ok) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }
-                        xp[0] = pack2(x0.x, x0.y); xp[1] = pack2(x0.z, x0.w); xp[2] = pack2(x1.x, x1.y); xp[3] = pack2(x1.z, x1.w);
-                    }
-                    if (!c.dead) c.ready = peek_tile_after_next(S, c);
-                    if (have) { flush_group(p, S, c, gq, pend, pend_real, ss, dump_a, lane); have = false; }
-#pragma unroll
-                    for (int r = 0; r < kRows; ++r) fma8(w[r], xp, acc[r]);
-                    if (lane == 0) mbar_arrive(S.empty_a + c.ring.sl * 8);       // (the FMAs above consumed every lane's loads)
-                    mine_any = true;
-                    if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
-                }
+                const int ncols = min(CT, C - col0);
+                const bool ok = col < ncols;                          // lanes past a short tile's last column read column 0 against zeros
+                const uint32_t stride = (uint32_t)ncols * 2u;
+                const uint32_t wa = S.slots_a + c.ring.sl * kSlotBytes + (ok ? (uint32_t)col << 1 : 0u);
+                wait_full(p, S, c, 3);
+                if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
+                const uint32_t eb = S.empty_a + c.ring.sl * 8;
                 c.ring.advance();
-            }
-            if (have) flush_group(p, S, c, gq, pend, pend_real, ss, dump_a, lane);     // (a row group without a tile of ours in between)
+                TileW t;
+                unsigned long long xp[4];
+                xs_ld(ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4), ok, xp);
+                tile_ldw(wa, stride, t);
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-                float lo, hi;
-                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[r]));
-                pend[r] = lo + hi;
+                for (int r = 0; r < kRows; ++r) fma8(t.w[r], xp, acc[r]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(eb);
+                if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
             }
-            have = true;
-            pend_real = mine_any;
         }
+        float v[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[r]));
+            v[r] = lo + hi;
+        }
+        flush_group(p, S, c, gq, v, ss, dump_a, lane);
     }
-    if (have) flush_group(p, S, c, gq, pend, pend_real, ss, dump_a, lane);
     mark(pm, p, phase_idx, PROF_LAST_TILE);
-    bar_sync(BAR_PAIR0 + cw, 64);                 // both warps are done reading xs before the next prologue overwrites it
     return pack_state(gq, c.ring);
 }
 
@@ -839,25 +824,23 @@ __device__ __forceinline__ float wait_flagged1(const DecParams& p, const unsigne
 
 // Single-query attention over this CTA's (head, KV split) units (cmdbuf_mat_mul QK^T * 1/sqrt(D),
 // cmdbuf_row_softmax, cmdbuf_mat_mul P*V; th-llama.cpp:365-380).  Every warp runs its own online
-// softmax over the positions j = warp (mod 16) of each K/V tile pair -- no CTA barrier per tile -- and
-// the 16 warps are merged once per unit.  The split results {m, l, o[D]} go to p.part; the Wo
+// softmax over the positions j = warp (mod 8) of each K/V tile pair -- no CTA barrier per tile -- and
+// the 8 warps are merged once per unit.  The split results {m, l, o[D]} go to p.part; the Wo
 // prologue merges the splits of a head.
-__device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, unsigned long long state, int layer) {
+__device__ __forceinline__ unsigned long long math_att_phase(const DecParams& p, unsigned long long state, int layer) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1);
-    const unsigned g = (unsigned)(mw >> 3);
-    Cons c{{0u, 0u, 0u}, false, false};
+    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31;
+    Cons c{{0u, 0u}, false};
     unsigned gq;
     unpack_state(state, gq, c.ring);
-    unsigned pair = 0;                                // K/V tile pairs of this phase so far: pair i belongs to group i % 2
     const thk_llama_layer L = p.layers[layer];
     const AttSched a = make_att(p);
     const int D = p.head_dim;
     const float scale = 1.0f / sqrtf((float)D);
     const bool act = lane < (D >> 2);
-    float* sc_o = S.red + kAttScratchOff;             // [16][128]
-    float* sc_m = sc_o + kMathWarps * kMaxHeadDim;    // [16]
-    float* sc_l = sc_m + kMathWarps;                  // [16]
+    float* sc_o = S.red + kAttScratchOff;             // [8][128]
+    float* sc_m = sc_o + kMathWarps * kMaxHeadDim;    // [8]
+    float* sc_l = sc_m + kMathWarps;                  // [8]
     float* sc_kn = sc_l + kMathWarps;                 // [128] the new position's K row (warp 0 only)
     float* sc_vn = sc_kn + kMaxHeadDim;               // [128] ... and V row
     for (int u = blockIdx.x; u < p.Hl * a.S; u += gridDim.x) {
@@ -879,9 +862,8 @@ __device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, un
         }
         float m = -INFINITY, lsum = 0.f;
         float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int pos = pa; pos < pb; pos += p.att_tpos, ++pair) {
+        for (int pos = pa; pos < pb; pos += p.att_tpos) {
             const int np = min(p.att_tpos, pb - pos);
-            if ((pair & 1u) != g) { c.ring.advance(); c.ring.advance(); continue; }     // the other group's pair
             // the K tile and the V tile of these positions sit in consecutive slots
             wait_full(p, S, c, 4);
             const float* kt = (const float*)(S.slots + c.ring.sl * kSlotBytes);
@@ -890,11 +872,11 @@ __device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, un
             wait_full(p, S, cv, 5);
             const float* vt = (const float*)(S.slots + cv.ring.sl * kSlotBytes);
             c.dead = c.dead || cv.dead;
-            for (int j0 = cw; j0 < np; j0 += 4 * kGroupWarps) {      // 4 positions of this warp per round
+            for (int j0 = mw; j0 < np; j0 += 4 * kMathWarps) {      // 4 positions of this warp per round
                 float s[4];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const int j = j0 + t * kGroupWarps;
+                    const int j = j0 + t * kMathWarps;
                     s[t] = (act && j < np) ? dot4(q4, *(const float4*)(kt + j * D + (lane << 2))) : 0.f;
                 }
 #pragma unroll
@@ -904,14 +886,14 @@ __device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, un
                 }
                 float mx = -INFINITY;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) { s[t] = (j0 + t * kGroupWarps < np) ? s[t] * scale : -INFINITY; mx = fmaxf(mx, s[t]); }
+                for (int t = 0; t < 4; ++t) { s[t] = (j0 + t * kMathWarps < np) ? s[t] * scale : -INFINITY; mx = fmaxf(mx, s[t]); }
                 const float m_new = fmaxf(m, mx);
                 const float corr = expf(m - m_new);
                 lsum *= corr; o4.x *= corr; o4.y *= corr; o4.z *= corr; o4.w *= corr;
                 m = m_new;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
-                    const int j = j0 + t * kGroupWarps;
+                    const int j = j0 + t * kMathWarps;
                     if (j < np) {
                         const float pj = expf(s[t] - m);
                         lsum += pj;
@@ -942,7 +924,7 @@ __device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, un
             o4.x = fmaf(pj, v4.x, o4.x * corr); o4.y = fmaf(pj, v4.y, o4.y * corr);
             o4.z = fmaf(pj, v4.z, o4.z * corr); o4.w = fmaf(pj, v4.w, o4.w * corr);
         }
-        // merge the 16 warps (fixed order -> deterministic)
+        // merge the 8 warps (fixed order -> deterministic)
         if (act) *(float4*)(sc_o + mw * kMaxHeadDim + (lane << 2)) = o4;
         if (lane == 0) { sc_m[mw] = m; sc_l[mw] = lsum; }
         bar_sync(BAR_MATH, kMathThreads);
@@ -967,9 +949,10 @@ __device__ __noinline__ unsigned long long math_att_phase(const DecParams& p, un
 }
 
 // ---- prologues: stage the phase's activation vector in shared memory (permuted layout) ----
-// Chunk c of every K tile is multiplied by the two warps (c, 0) and (c, 1) only, and within a chunk a lane only ever
-// touches its own 8 columns.  Warp (c, h) stages the K tiles kt = h, h + 2, ... of chunk c; a 64-thread named barrier
-// (BAR_PAIR0 + c) publishes them to its partner.  No CTA-wide barrier, no cross-chunk traffic.
+// A math warp only ever multiplies against ITS columns of the activation vector: chunk cw of every K tile, and within a
+// chunk a lane only its own 8 columns.  So the staged vector xs is lane-private storage: every lane loads, transforms and
+// stores exactly the values it will read back -- no CTA barrier, no cross-warp traffic, and a warp starts on its first
+// tile as soon as its own loads have landed.
 __device__ __forceinline__ float4 emb_f4(const uint16_t* row, int i) {
     const uint2 u = __ldg((const uint2*)(row + i));
     const float2 a = h2_to_f2(u.x), b = h2_to_f2(u.y);
@@ -982,22 +965,22 @@ __device__ __forceinline__ float4 emb_f4(const uint16_t* row, int i) {
 // hand-off record).  fsrc != nullptr: v comes from a flagged vector (waits for `epoch`); else v is the embedding row
 // (first phase of a launch), which is also published as the flagged residual stream `xf_out` (epoch `epoch`), every
 // element by exactly one CTA.  The gain was L2-prefetched during the previous phase.
-__device__ __noinline__ float prologue_norm(const DecParams& p, int ph, const uint16_t* emb_row, const unsigned long long* fsrc, unsigned epoch,
+__device__ __forceinline__ float prologue_norm(const DecParams& p, int ph, const uint16_t* emb_row, const unsigned long long* fsrc, unsigned epoch,
                                             const float* gain, unsigned long long* xf_out) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1), rh = mw >> 3;   // rh: the warp's group
+    const int ct = (int)threadIdx.x - kMathBase, cw = ct >> 5, lane = ct & 31;
     const PhaseDesc& d = p.ph[ph];
     bool dead = false;
     const int n = d.C;
     const int lcol = (cw << 8) + (lane << 3);                 // this lane's first column inside a K tile
     const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
     float ss = 0.f;
-    for (int kt0 = rh; kt0 < d.KT; kt0 += 4) {                // this warp's K tiles kt0 and kt0 + 2 per L2 round trip
+    for (int kt0 = 0; kt0 < d.KT; kt0 += 2) {                 // two K tiles per L2 round trip
         float4 v[4], g[4];
         int col[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const int kt = kt0 + 2 * u;
+            const int kt = kt0 + u;
             const int c = kt * d.CT + lcol;
             col[u] = (kt < d.KT && lcol < d.CT && c < n) ? c : -1;
             if (col[u] >= 0) {
@@ -1026,7 +1009,7 @@ __device__ __noinline__ float prologue_norm(const DecParams& p, int ph, const ui
                         st_flagged(xf_out + i, t.x, epoch); st_flagged(xf_out + i + 1, t.y, epoch);
                         st_flagged(xf_out + i + 2, t.z, epoch); st_flagged(xf_out + i + 3, t.w, epoch);
                     }
-                    sts128f(xa + (uint32_t)(((kt0 + 2 * u) * d.CT) << 2) + 512u * hh, make_float4(t.x * gg.x, t.y * gg.y, t.z * gg.z, t.w * gg.w));
+                    sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2) + 512u * hh, make_float4(t.x * gg.x, t.y * gg.y, t.z * gg.z, t.w * gg.w));
                 }
             }
         }
@@ -1034,19 +1017,19 @@ __device__ __noinline__ float prologue_norm(const DecParams& p, int ph, const ui
     return warp_sum(ss);
 }
 // xs <- the FFN hidden vector for W2, from the flagged vector (waits for `epoch`)
-__device__ __noinline__ void prologue_copy(const DecParams& p, int ph, const unsigned long long* fsrc, unsigned epoch) {
+__device__ __forceinline__ void prologue_copy(const DecParams& p, int ph, const unsigned long long* fsrc, unsigned epoch) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1), rh = mw >> 3;   // rh: the warp's group
+    const int ct = (int)threadIdx.x - kMathBase, cw = ct >> 5, lane = ct & 31;
     const PhaseDesc& d = p.ph[ph];
     bool dead = false;
     const int n = d.C;
     const int lcol = (cw << 8) + (lane << 3);
     const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
-    for (int kt0 = rh; kt0 < d.KT; kt0 += 6) {                // this warp's K tiles kt0, kt0 + 2, kt0 + 4 per L2 round trip
+    for (int kt0 = 0; kt0 < d.KT; kt0 += 3) {                 // three K tiles per L2 round trip
         int col[3];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-            const int kt = kt0 + 2 * u;
+            const int kt = kt0 + u;
             const int c = kt * d.CT + lcol;
             col[u] = (kt < d.KT && lcol < d.CT && c < n) ? c : -1;
         }
@@ -1055,8 +1038,8 @@ __device__ __noinline__ void prologue_copy(const DecParams& p, int ph, const uns
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             if (col[u] >= 0) {
-                sts128f(xa + (uint32_t)(((kt0 + 2 * u) * d.CT) << 2), flagged_f4(e + 8 * u));
-                sts128f(xa + (uint32_t)(((kt0 + 2 * u) * d.CT) << 2) + 512u, flagged_f4(e + 8 * u + 4));
+                sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2), flagged_f4(e + 8 * u));
+                sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2) + 512u, flagged_f4(e + 8 * u + 4));
             }
         }
     }
@@ -1066,15 +1049,15 @@ __device__ __noinline__ void prologue_copy(const DecParams& p, int ph, const uns
 // in flight together (~0.6 us per L2 round trip under the weight stream).  (A flagged, barrier-free version of the
 // QKV -> attention -> Wo hand-overs was built and measured slower: 2.69 -> 2.96 ms/token -- the polling of 128 split
 // records by every CTA costs more than the two grid barriers it removes.)
-__device__ __noinline__ void prologue_att_merge(const DecParams& p, int ph) {
+__device__ __forceinline__ void prologue_att_merge(const DecParams& p, int ph) {
     const Smem S = smem_view();
-    const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31, cw = mw & (kGroupWarps - 1), rh = mw >> 3;   // rh: the warp's group
+    const int ct = (int)threadIdx.x - kMathBase, cw = ct >> 5, lane = ct & 31;
     const PhaseDesc& d = p.ph[ph];
     const AttSched a = make_att(p);
     const int D = p.head_dim, ps = part_stride(p);
     const int lcol = (cw << 8) + (lane << 3);
     const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
-    for (int kt = rh; kt < d.KT; kt += 2) {
+    for (int kt = 0; kt < d.KT; ++kt) {
         const int c = kt * d.CT + lcol;
         if (lcol >= d.CT || c >= d.C) continue;
         const int h = c / D, dd = c - h * D;                  // 8 consecutive columns never straddle a head (D % 8 == 0)
@@ -1203,9 +1186,9 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
     const PhaseDesc& d = p.ph[ph];
     const int D = p.head_dim, tp_size = kTP ? p.tp_size : 1, tp_rank = kTP ? p.tp_rank : 0, n_ctx = p.n_ctx, n_past = p.n_past;
     const int nsub = d.paired ? 2 : 1;
-    // lane (r, q): row r = lane & 7 of the row group, math warps 4q .. 4q + 3
+    // lane (r, q): row r = lane & 7 of the row group, math warps 2q and 2q + 1
     const int rr = lane & 7, qq = lane >> 3;
-    const uint32_t my_a = S.red_a + (uint32_t)(((4 * qq) * kRecFloats + rr) * 4);
+    const uint32_t my_a = S.red_a + (uint32_t)(((2 * qq) * kRecFloats + rr) * 4);
     const bool has_resid = (kind == EPI_WO || kind == EPI_W2) && !kTP;
     const bool need_scale = (kind == EPI_QKV || kind == EPI_W13 || kind == EPI_OUT);
     bool have_scale = false;
@@ -1244,11 +1227,11 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
                 }
             }
             const uint32_t src = my_a + buf * (uint32_t)(kRedFloats * 4);
-            float y = (lds32f(src) + lds32f(src + kRecFloats * 4)) + (lds32f(src + 2 * kRecFloats * 4) + lds32f(src + 3 * kRecFloats * 4));
+            float y = lds32f(src) + lds32f(src + kRecFloats * 4);
             y += __shfl_xor_sync(0xffffffffu, y, 8);
             y += __shfl_xor_sync(0xffffffffu, y, 16);      // every lane: total of row (lane & 7)
             if (need_scale && !have_scale) {
-                // RMSNorm scale of this phase's input (th.cpp:1153-1200): every hand-off record carries the sixteen warps'
+                // RMSNorm scale of this phase's input (th.cpp:1153-1200): every hand-off record carries the eight warps'
                 // shares of sum(v^2); added in warp order: deterministic.
                 float tot = 0.f;
 #pragma unroll
@@ -1458,37 +1441,41 @@ __global__ void __launch_bounds__(kThreads, 1) decode_kernel(const __grid_consta
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNumSlots; ++i) {
             mbar_init(S.full_a + i * 8, 1);
-            mbar_init(S.empty_a + i * 8, kGroupWarps);          // a tile is consumed by one group
+            mbar_init(S.empty_a + i * 8, kMathWarps);
         }
         for (int i = 0; i < kDumpBufs; ++i) {
-            mbar_init(S.red_full_a + i * 8, kMathWarps * kRecArrivals);
+            mbar_init(S.red_full_a + i * 8, kMathWarps);
             mbar_init(S.red_free_a + i * 8, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (blockIdx.x == 0) *p.bar_next = 0u;   // arm the next launch's barrier counter
     }
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&p);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&S.misc->prm);
-        for (int i = threadIdx.x; i < (int)(sizeof(DecParams) / 4); i += kThreads) dst[i] = src[i];
-        if (PROF(p) && threadIdx.x < (kMathWarps + kSvcWarps) * 4) (&S.misc->wstat[0][0])[threadIdx.x] = 0ull;
-    }
+    if (PROF(p) && threadIdx.x < (kMathWarps + kSvcWarps) * 4) (&S.misc->wstat[0][0])[threadIdx.x] = 0ull;
     // A token id outside the vocabulary (th-llama.cpp:606 asserts) is the same on every CTA (and every rank): the whole
     // grid leaves before any phase starts, nothing waits on anything, and the host reads THK_E_INVALID from the status word.
     if (tok < 0 || tok >= p.n_vocab) {
         if (threadIdx.x == 0 && blockIdx.x == 0) raise_abort(p, 0x300u, (unsigned)tok, 0u);
         return;
     }
-    if (threadIdx.x >= kSvcBase + 64 && threadIdx.x < kSvcBase + 69) {            // (lanes of the reducer warp)
+    if ((int)threadIdx.x >= kSvcBase + 64 && (int)threadIdx.x < kSvcBase + 69) {  // (lanes of the reducer warp)
         const int ph = (int)threadIdx.x - (kSvcBase + 64);
         RowIt::share(p.ph[ph], gridDim.x, blockIdx.x, S.misc->range[ph][0], S.misc->range[ph][1]);
+        RowIt it;
+        int n = 0;
+        for (it.init_range(S.misc->range[ph][0], S.misc->range[ph][1], p.ph[ph]); it.valid(); it.next()) ++n;
+        S.misc->niter[ph] = n * (p.ph[ph].paired ? 2 : 1);
     }
     __syncthreads();
-    const int sw = ((int)threadIdx.x - kSvcBase) >> 5;             // service warp index (meaningless for math threads)
-    if ((int)threadIdx.x >= kMathBase && (int)threadIdx.x < kMathBase + kMathThreads) math_main(S.misc->prm, tok);   // (the shared-memory copy of the parameters)
-    else if (sw == 0) producer_main(p, S);
-    else if (sw == 1) epi_main<kTP>(p, S);
-    else if (kTP) reducer_main(p, tok);
+    if ((int)threadIdx.x >= kSvcBase) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
+        const int sw = ((int)threadIdx.x - kSvcBase) >> 5;         // service warp index
+        if (sw == 0) producer_main(p, S);
+        else if (sw == 1) epi_main<kTP>(p, S);
+        else if (sw == 2 && kTP) reducer_main(p, tok);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kMathRegs));
+        math_main(p, tok);
+    }
 }
 
 size_t decode_smem_bytes(int max_vec) {

@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         L.tho_model_hparams.restype = C.c_void_p
         L.tho_model_hparams.argtypes = [C.c_void_p]
         L.tho_num_threads.restype = C.c_int
+        L.tho_set_num_threads.argtypes = [C.c_int]
         L.tho_set_strict_order.argtypes = [C.c_int]
         _lib = L
     return _lib
@@ -404,6 +405,18 @@ def fill_kv(seed, tid, n):
 
 def num_threads() -> int:
     return lib().tho_num_threads()
+
+
+def use_all_cores() -> int:
+    """Run the OpenMP loops on every core this process may use, whatever OMP_NUM_THREADS says (torchrun exports
+    OMP_NUM_THREADS=1 to every rank).  Returns the thread count in effect."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().tho_set_num_threads(int(n))
+    return num_threads()
 
 
 # ---- oracle/_ref: the reference's own host code (present only where it was built) ----

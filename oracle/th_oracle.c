@@ -31,6 +31,14 @@ int tho_num_threads(void) {
     return 1;
 #endif
 }
+/* bench.py's CPU arms set this explicitly: torchrun exports OMP_NUM_THREADS=1 to every rank */
+void tho_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 /* ------------------------------------------------------------------------------------------
  * fp16 <-> fp32: the Maratyszcza bit trick the reference copied from ggml (th.cpp:291-359);

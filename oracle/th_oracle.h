@@ -117,6 +117,7 @@ tho_model* tho_load_ggjt(const char* path, int32_t n_ctx);
 int        tho_write_ggjt(const tho_model* m, const char* path);
 
 int  tho_num_threads(void);
+void tho_set_num_threads(int n);   /* omp_set_num_threads: overrides OMP_NUM_THREADS (torchrun sets it to 1) */
 void tho_set_strict_order(int on);  /* 1 (default): shader summation order; 0: plain sequential */
 
 #ifdef __cplusplus

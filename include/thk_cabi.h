@@ -211,6 +211,9 @@ int thk_decoder_set_peers(thk_decoder* dec, void* const* peer_bufs, void* const*
  * 404, 429-430, 444). tcgen05 + TMEM + TMA; X is split into f16 hi + lo terms so the result keeps
  * f32-activation accuracy. */
 int thk_gemm_f16_tc(thk_ctx* ctx, const float* X, const uint16_t* W, float* Y, int64_t M, int64_t N, int64_t K);
+/* sizes the context's hi/lo workspace for X up to [max_M, max_K] once (post_load_init_model allocates all working buffers
+ * at load time, th-llama-loader.cpp:330-435), so that thk_gemm_f16_tc itself never allocates */
+int thk_gemm_reserve(thk_ctx* ctx, int64_t max_M, int64_t max_K);
 /* blocks on the stream; THK_E_TIMEOUT if a GEMM launch hit its in-kernel watchdog */
 int thk_gemm_check(thk_ctx* ctx);
 

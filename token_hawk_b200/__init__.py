@@ -92,6 +92,7 @@ def kernels() -> C.CDLL:
             "thk_decoder_set_peers": [vp, C.POINTER(vp), C.POINTER(vp), C.c_int],
             "thk_gemm_f16_tc": [vp, vp, vp, vp, i64, i64, i64],
             "thk_gemm_check": [vp],
+            "thk_gemm_reserve": [vp, i64, i64],
             "thk_ipc_export": [vp, vp, C.POINTER(C.c_ubyte)],
             "thk_ipc_import": [vp, C.POINTER(C.c_ubyte), C.POINTER(vp)],
             "thk_ipc_close": [vp, vp],

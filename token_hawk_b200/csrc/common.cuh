@@ -14,6 +14,12 @@ struct thk_ctx {
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
     size_t total_mem = 0;
+    // tensor-core GEMM (gemm_tc.cu): hi/lo split workspace and watchdog status word of THIS context -- two contexts on one
+    // device (or two models on different streams) never share operands in flight
+    void* gemm_ws = nullptr;
+    size_t gemm_ws_bytes = 0;
+    unsigned* gemm_status = nullptr;
+    bool gemm_attr_set = false;       // cudaFuncSetAttribute is per device; a context belongs to one device
 };
 
 void thk_set_error(const char* fmt, ...);

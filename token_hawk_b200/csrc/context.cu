@@ -60,7 +60,10 @@ extern "C" int thk_destroy(thk_ctx* ctx) {
     THK_ENTER(ctx);
     if (!ctx) return THK_OK;
     cudaSetDevice(ctx->device);
-    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->gemm_ws);
+    cudaFree(ctx->gemm_status);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return THK_OK;
 }

@@ -201,8 +201,37 @@ int make_map(EncodeTiledFn fn, CUtensorMap* map, const void* base, int64_t rows,
 
 }  // namespace
 
-struct GemmWorkspace { void* buf = nullptr; size_t bytes = 0; unsigned* status = nullptr; };
-static GemmWorkspace g_ws[16];   // per device ordinal; grown on demand, owned by the library (kernels never allocate)
+static EncodeTiledFn lookup_encode() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    return (EncodeTiledFn)fn;
+}
+
+// The hi/lo split workspace and the status word belong to the context (one stream): thk_gemm_reserve sizes them once at
+// model load, so that thk_gemm_f16_tc itself never allocates ("kernels never allocate", thk_cabi.h); a larger request
+// than reserved still works (drain this context's stream, grow) but is not the intended path.
+static int gemm_workspace(thk_ctx* ctx, size_t need) {
+    if (ctx->gemm_ws_bytes < need) {
+        THK_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->gemm_ws);
+        ctx->gemm_ws = nullptr; ctx->gemm_ws_bytes = 0;
+        THK_CUDA(cudaMalloc(&ctx->gemm_ws, need));
+        ctx->gemm_ws_bytes = need;
+    }
+    if (!ctx->gemm_status) { THK_CUDA(cudaMalloc(&ctx->gemm_status, 16)); THK_CUDA(cudaMemsetAsync(ctx->gemm_status, 0, 16, ctx->stream)); }
+    if (!ctx->gemm_attr_set) {
+        THK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kStages * kStageBytes + 1024)));
+        ctx->gemm_attr_set = true;
+    }
+    return THK_OK;
+}
+
+extern "C" int thk_gemm_reserve(thk_ctx* ctx, int64_t max_M, int64_t max_K) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx && max_M > 0 && max_K > 0, "thk_gemm_reserve: bad argument");
+    return gemm_workspace(ctx, (size_t)max_M * max_K * 2 * 2);
+}
 
 extern "C" int thk_gemm_f16_tc(thk_ctx* ctx, const float* X, const uint16_t* W, float* Y, int64_t M, int64_t N, int64_t K) {
     THK_ENTER(ctx);
@@ -210,25 +239,11 @@ extern "C" int thk_gemm_f16_tc(thk_ctx* ctx, const float* X, const uint16_t* W, 
     THK_CHECK_ARG(M > 0 && N > 0 && K > 0, "thk_gemm_f16_tc: bad shape");
     THK_CHECK_ARG(N % BN == 0, "thk_gemm_f16_tc: N must be a multiple of %d (N=%lld)", BN, (long long)N);
     THK_CHECK_ARG(K % BK == 0, "thk_gemm_f16_tc: K must be a multiple of %d (K=%lld)", BK, (long long)K);
-    THK_CHECK_ARG(ctx->device < 16, "thk_gemm_f16_tc: device ordinal too large");
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        THK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (qres != cudaDriverEntryPointSuccess || !fn) { thk_set_error("cuTensorMapEncodeTiled not available in this driver"); return THK_E_UNSUPPORTED; }
-        encode = (EncodeTiledFn)fn;
-    }
-    GemmWorkspace& ws = g_ws[ctx->device];
-    const size_t need = (size_t)M * K * 2 * 2;
-    if (ws.bytes < need) {
-        THK_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ws.buf) cudaFree(ws.buf);
-        THK_CUDA(cudaMalloc(&ws.buf, need));
-        ws.bytes = need;
-    }
-    if (!ws.status) { THK_CUDA(cudaMalloc(&ws.status, 16)); THK_CUDA(cudaMemset(ws.status, 0, 16)); }
-    __half* hi = (__half*)ws.buf;
+    static const EncodeTiledFn encode = lookup_encode();        // (thread-safe: C++11 static initialisation)
+    if (!encode) { thk_set_error("cuTensorMapEncodeTiled not available in this driver"); return THK_E_UNSUPPORTED; }
+    int rc = gemm_workspace(ctx, (size_t)M * K * 2 * 2);
+    if (rc) return rc;
+    __half* hi = (__half*)ctx->gemm_ws;
     __half* lo = hi + (size_t)M * K;
     {
         int64_t blocks = ((int64_t)M * K + 255) / 256;
@@ -237,14 +252,12 @@ extern "C" int thk_gemm_f16_tc(thk_ctx* ctx, const float* X, const uint16_t* W, 
         THK_LAUNCH_CHECK();
     }
     GemmParams p{};
-    int rc = make_map(encode, &p.map_hi, hi, M, K, BM);
+    rc = make_map(encode, &p.map_hi, hi, M, K, BM);
     if (!rc) rc = make_map(encode, &p.map_lo, lo, M, K, BM);
     if (!rc) rc = make_map(encode, &p.map_w, W, N, K, BN);
     if (rc) return rc;
-    p.Y = Y; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.status = ws.status;
+    p.Y = Y; p.M = (int)M; p.N = (int)N; p.K = (int)K; p.status = ctx->gemm_status;
     const size_t smem = (size_t)kStages * kStageBytes + 1024;
-    static bool attr_set = false;
-    if (!attr_set) { THK_CUDA(cudaFuncSetAttribute(gemm_f16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
     dim3 grid((unsigned)(N / BN), (unsigned)((M + BM - 1) / BM));
     gemm_f16_tc_kernel<<<grid, 128, smem, ctx->stream>>>(p);
     THK_LAUNCH_CHECK();
@@ -254,12 +267,11 @@ extern "C" int thk_gemm_f16_tc(thk_ctx* ctx, const float* X, const uint16_t* W, 
 // reports a watchdog abort of the GEMM kernel (bounded mbarrier waits); blocks on the stream
 extern "C" int thk_gemm_check(thk_ctx* ctx) {
     THK_ENTER(ctx);
-    THK_CHECK_ARG(ctx && ctx->device < 16, "thk_gemm_check: bad ctx");
-    GemmWorkspace& ws = g_ws[ctx->device];
-    if (!ws.status) return THK_OK;
+    THK_CHECK_ARG(ctx, "thk_gemm_check: bad ctx");
+    if (!ctx->gemm_status) return THK_OK;
     unsigned st = 0;
-    THK_CUDA(cudaMemcpyAsync(&st, ws.status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    THK_CUDA(cudaMemcpyAsync(&st, ctx->gemm_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
     THK_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (st) { thk_set_error("gemm_f16_tc_kernel aborted: code 0x%x (mbarrier wait timed out)", st); cudaMemsetAsync(ws.status, 0, 4, ctx->stream); return THK_E_TIMEOUT; }
+    if (st) { thk_set_error("gemm_f16_tc_kernel aborted: code 0x%x (mbarrier wait timed out)", st); cudaMemsetAsync(ctx->gemm_status, 0, 4, ctx->stream); return THK_E_TIMEOUT; }
     return THK_OK;
 }

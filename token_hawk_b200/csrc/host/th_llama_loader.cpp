@@ -7,6 +7,7 @@
 #include "th/th-llama-loader.hpp"
 
 #include <string.h>
+#include <algorithm>
 
 #include <fstream>
 
@@ -180,6 +181,9 @@ void post_load_init_model(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Ll
     }
     m->ffWorking[0] = TensorBuffer(TensorShape{0, 0, m->n_batch, F}, TensorType_F32, device);   // :351-352
     m->ffWorking[1] = TensorBuffer(TensorShape{0, 0, m->n_batch, F}, TensorType_F32, device);
+    // workspace of the batched-prompt GEMM (f16 hi/lo split of up to n_batch activation rows), sized once here like every
+    // other working buffer so that the evaluation path never allocates
+    if (m->tp_size == 1 && thk_gemm_reserve(device, m->n_batch, std::max<int64_t>(E, F)) != THK_OK) fprintf(stderr, "post_load_init_model: %s\n", thk_last_error());
     m->out = TensorBuffer(TensorShape{0, 0, 1, Vl}, TensorType_F32, device);                    // :360
     m->outScratch = TensorBuffer(TensorShape{0, 0, 1, Vl}, TensorType_F32, device);
     void* p = nullptr;

@@ -326,11 +326,20 @@ def main():
         marks, prod = model.profile(True, fetch=True)
         model.profile(False)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"timeline_ctx{args.ctx}.npz"), marks=marks, prod=prod,
+        np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"timeline_ctx{args.ctx}_n{world}_r{rank}.npz"), marks=marks, prod=prod,
                             n_layer=args.layers, ctx=args.ctx)
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import analyze_timeline
-        print("PHASES " + json.dumps(analyze_timeline.summarize(marks, prod, args.layers, args.ctx)), file=sys.stderr)
+        if rank == 0:
+            summ = analyze_timeline.summarize(marks, prod, args.layers, args.ctx)
+            keys = ("us", "arrive_skew_us", "barrier_latency_us", "prologue_us", "first_tile_wait_us", "tile_span_med_us", "tile_span_max_us")
+            brief = {k: {kk: round(vv, 2) for kk, vv in v.items() if kk in keys} for k, v in summ.items() if isinstance(v, dict)}
+            print(f"PHASES n_gpus={world} " + json.dumps(brief) + f" kernel_us {summ['kernel_us']:.1f}", file=sys.stderr)
+            w = model.last_wait_cycles.astype(float)
+            life = w[:, :, 3].clip(min=1)
+            for role, sl in (("math", slice(0, 8)), ("producer", slice(8, 9)), ("epilogue", slice(9, 10)), ("reducer", slice(10, 11))):
+                fr = [float(np.median(w[:, sl, i] / life[:, sl])) for i in range(3)]
+                print(f"WAITS {role:9s} share of lifetime waiting: ring {100*fr[0]:5.1f}%, handoff {100*fr[1]:5.1f}%, poll {100*fr[2]:5.1f}%", file=sys.stderr)
 
     peak, peak_src = load_peaks()
 

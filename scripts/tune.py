@@ -77,7 +77,7 @@ def main():
                 life = w[:, :, 3].clip(min=1)
                 import numpy as np
                 names = ["ring", "handoff", "poll"]
-                for role, sl in (("math", slice(0, 16)), ("producer", slice(16, 17)), ("epilogue", slice(17, 18))):
+                for role, sl in (("math", slice(0, 8)), ("producer", slice(8, 9)), ("epilogue", slice(9, 10)), ("reduce", slice(10, 12))):
                     fr = [float(np.median(w[:, sl, i] / life[:, sl])) for i in range(3)]
                     print(f"WAITS {tag} {role:9s} lifetime {np.median(life[:, sl])/1e6:6.3f} Mcycles; share waiting: "
                           + ", ".join(f"{n} {100*f:5.1f}%" for n, f in zip(names, fr)), flush=True)

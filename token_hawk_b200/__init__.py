@@ -407,7 +407,7 @@ class LlamaModel:
         when fetch is set; slots: 0 phase start, 1 prologue end, 2 first tile ready, 3 last tile done,
         4 barrier arrive, 5 after fence, 6 consumer ring-wait cycles."""
         grid = self.dev.sm_count
-        n0, n1, nt, nw = grid * 256 * 8, grid * 4, grid * 64, grid * 19 * 4
+        n0, n1, nt, nw = grid * 256 * 8, grid * 4, grid * 64, grid * 12 * 4
         n = n0 + n1 + 2 * nt + nw if fetch else 0
         buf = np.zeros(max(n, 1), dtype=np.uint64)
         if host().capi_profile(self.h, int(enable), buf.ctypes.data_as(C.POINTER(C.c_uint64)) if fetch else None, n):
@@ -418,7 +418,7 @@ class LlamaModel:
         self.last_tile_times = (buf[n0 + n1:n0 + n1 + nt].reshape(grid, 64).astype(np.int64),
                                 buf[n0 + n1 + nt:n0 + n1 + 2 * nt].reshape(grid, 64).astype(np.int64))
         # cycles every warp spent waiting: [cta][warp: 16 math, producer, epilogue, reducer][ring, hand-off, poll, lifetime]
-        self.last_wait_cycles = buf[n0 + n1 + 2 * nt:].reshape(grid, 19, 4).astype(np.int64)
+        self.last_wait_cycles = buf[n0 + n1 + 2 * nt:].reshape(grid, 12, 4).astype(np.int64)
         return buf[:n0].reshape(grid, 256, 8).astype(np.int64), buf[n0:n0 + n1].reshape(grid, 4).astype(np.int64)
 
     def tokenize(self, text: str, add_bos: bool = True):

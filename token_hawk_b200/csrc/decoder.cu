@@ -58,6 +58,9 @@ constexpr int kRows = 8;                              // rows per row group (= p
 constexpr int kMaxTilePos = 128;                      // attention: positions per tile cap
 constexpr int kMaxHeadDim = 128;
 constexpr int kMaxSplit = 8;                          // attention: KV splits per head cap
+#ifndef THK_COPY_CHUNKS
+#define THK_COPY_CHUNKS 3
+#endif
 constexpr int kDumpBufs = 8;                          // row-group hand-off ring between the math warps and the epilogue warp
 constexpr int kMaxOwn = 4;                            // tensor parallel: residual elements per reducer lane (n_embd <= 128 * grid)
 enum NamedBarrier { BAR_ALL = 1, BAR_MATH = 2, BAR_PRE = 3 };
@@ -772,17 +775,21 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 
 // Flagged-vector read: this lane's 8 columns of NCH chunks (chunk u starts at element col[u]; col[u] < 0: no such chunk),
 // all loads in flight together, repeated until every element carries `epoch` -- that IS the synchronisation with the
-// CTAs that produce the vector (no grid barrier on these transitions).  After a stale read the lane first spins on the one
-// stale element (8 bytes per round instead of 64 * NCH), then reads everything again.  Bounded by the watchdog.
+// CTAs that produce the vector (no grid barrier on these transitions).  After a stale read only the stale chunks are read
+// again (tune poll_single: 0 = everything again, 1 = spin on the one stale element, then everything again).  Bounded by
+// the watchdog.
 template <int NCH>
 __device__ __forceinline__ void load_flagged(const DecParams& p, const unsigned long long* vec, const int (&col)[NCH], unsigned epoch,
                                              unsigned long long (&e)[NCH * 8], bool& dead) {
     unsigned long long t0 = 0;
     unsigned it = 0;
+    bool fresh[NCH];
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) fresh[u] = col[u] < 0;
     while (true) {
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
-            if (col[u] >= 0) {
+            if (!fresh[u]) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) ld_flagged2(vec + col[u] + 2 * j, e[u * 8 + 2 * j], e[u * 8 + 2 * j + 1]);
             }
@@ -790,13 +797,18 @@ __device__ __forceinline__ void load_flagged(const DecParams& p, const unsigned 
         int stale = -1;
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
-            if (col[u] >= 0) {
+            if (!fresh[u]) {
+                bool f = true;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if ((unsigned)(e[u * 8 + j] >> 32) != epoch && stale < 0) stale = col[u] + j;
+                for (int j = 0; j < 8; ++j) if ((unsigned)(e[u * 8 + j] >> 32) != epoch) { f = false; if (stale < 0) stale = col[u] + j; }
+                // poll_single == 2: a chunk that has arrived is kept; only the stale chunks are read again -- every re-read
+                // costs a whole L2 round trip BEHIND the weight stream's queue (1.3 us + 0.4 us per ring slot in flight,
+                // profiles/r2_timeline_and_experiments.md), so the last poll must also be the read that delivers the data
+                fresh[u] = f && p.poll_single == 2;
             }
         }
         if (stale < 0 || dead || p.nosync) break;
-        if (p.poll_single) {
+        if (p.poll_single == 1) {
             unsigned long long w;
             do {
                 w = ld_flagged1(vec + stale);
@@ -1025,18 +1037,20 @@ __device__ __forceinline__ void prologue_copy(const DecParams& p, int ph, const 
     const int n = d.C;
     const int lcol = (cw << 8) + (lane << 3);
     const uint32_t xa = S.xs_a + (uint32_t)(((cw << 8) + (lane << 2)) << 2);
-    for (int kt0 = 0; kt0 < d.KT; kt0 += 3) {                 // three K tiles per L2 round trip
-        int col[3];
+    constexpr int NCH = THK_COPY_CHUNKS;                      // K tiles per L2 round trip (6 would cover the 7B FFN vector in one, but spills:
+                                                              // local memory behind the weight stream cost 1.2 ms/token, measured)
+    for (int kt0 = 0; kt0 < d.KT; kt0 += NCH) {
+        int col[NCH];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < NCH; ++u) {
             const int kt = kt0 + u;
             const int c = kt * d.CT + lcol;
             col[u] = (kt < d.KT && lcol < d.CT && c < n) ? c : -1;
         }
-        unsigned long long e[24];
-        load_flagged<3>(p, fsrc, col, epoch, e, dead);
+        unsigned long long e[NCH * 8];
+        load_flagged<NCH>(p, fsrc, col, epoch, e, dead);
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < NCH; ++u) {
             if (col[u] >= 0) {
                 sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2), flagged_f4(e + 8 * u));
                 sts128f(xa + (uint32_t)(((kt0 + u) * d.CT) << 2) + 512u, flagged_f4(e + 8 * u + 4));
@@ -1386,6 +1400,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
 // epoch stamp makes the read the wait), adds them in rank order -- bitwise identical on every rank -- and publishes the
 // new residual value in the local flagged vector the next prologue (and nobody else) polls.
 __device__ void reducer_main(const DecParams& p, int tok) {
+    const long long t_life = wstat_t0();
     const int lane = (int)threadIdx.x & 31;
     const int E = p.n_embd, tp = p.tp_size;
     const int i0 = (int)(((long long)E * blockIdx.x) / gridDim.x), i1 = (int)(((long long)E * (blockIdx.x + 1)) / gridDim.x);
@@ -1410,6 +1425,7 @@ __device__ void reducer_main(const DecParams& p, int tok) {
                 unsigned long long e[8];
                 unsigned long long t0 = 0;
                 unsigned it = 0;
+                const long long tw0 = wstat_t0();
                 while (true) {
                     bool ok = true;
 #pragma unroll
@@ -1419,6 +1435,7 @@ __device__ void reducer_main(const DecParams& p, int tok) {
                     if (ok || dead || p.nosync) break;
                     if ((++it & 63u) == 0u && poll_watchdog(p.status, p.timeout_ns, t0, 0x600u | (unsigned)which, (unsigned)i, epoch)) dead = true;
                 }
+                wstat_add(WS_POLL, tw0);
                 float v = resid[j];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) if (r < tp) v += __uint_as_float((unsigned)e[r]);
@@ -1432,6 +1449,7 @@ __device__ void reducer_main(const DecParams& p, int tok) {
         const int i = i0 + lane + 32 * j;
         if (i < i1) p.x[i] = resid[j];
     }
+    wstat_flush(PROF(p), t_life);
 }
 
 template <bool kTP>
@@ -1624,7 +1642,7 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     p.prof_phase = -1;
     // tuning knobs (defaults = the measured best)
     p.l2_ahead = (unsigned)(getenv("THK_L2_AHEAD_KB") ? atoi(getenv("THK_L2_AHEAD_KB")) : 64) * 1024u;
-    p.poll_single = getenv("THK_POLL_SINGLE") ? atoi(getenv("THK_POLL_SINGLE")) : 1;
+    p.poll_single = getenv("THK_POLL_SINGLE") ? atoi(getenv("THK_POLL_SINGLE")) : 2;
     const int max_vec = p.n_embd > p.Fh ? p.n_embd : p.Fh;
     d->smem = decode_smem_bytes(max_vec);
     if (d->smem > 227 * 1024) {
@@ -1715,7 +1733,7 @@ extern "C" int thk_decoder_tune(thk_decoder* d, const char* key, int value) {
     THK_CHECK_ARG(d && key, "thk_decoder_tune: null argument");
     if (!strcmp(key, "l2_ahead_kb")) { THK_CHECK_ARG(value >= 0 && value <= 1024, "l2_ahead_kb out of range"); d->p.l2_ahead = (unsigned)value * 1024u; }
     else if (!strcmp(key, "prof_phase")) d->p.prof_phase = value;
-    else if (!strcmp(key, "poll_single")) d->p.poll_single = value != 0;
+    else if (!strcmp(key, "poll_single")) { THK_CHECK_ARG(value >= 0 && value <= 2, "poll_single: 0, 1 or 2"); d->p.poll_single = value; }
     else if (!strcmp(key, "nosync")) d->p.nosync = value != 0;
     else if (!strcmp(key, "timeout_ms")) { THK_CHECK_ARG(value > 0, "timeout_ms must be positive"); d->p.timeout_ns = (unsigned long long)value * 1000000ull; }
     else { thk_set_error("thk_decoder_tune: unknown key %s", key); return THK_E_INVALID; }

@@ -380,6 +380,24 @@ def vector_reduce(a, b, num_splits=8, refbug=False):
     return a
 
 
+def eval_trace(model: "Model", token: int, n_past: int):
+    """The commands tho_eval issues for one token, as lists: ["op", label, [operands], [uniform words]] or
+    ["copy", src, dst, dst_off, size] -- reference labels and buffer names (th_oracle.c, TR lines)."""
+    L = lib()
+    L.tho_trace_begin.restype = None
+    L.tho_trace_end.restype = C.c_char_p
+    L.tho_trace_begin()
+    model.eval([token], n_past)
+    out = []
+    for ln in L.tho_trace_end().decode().splitlines():
+        f = ln.split("|")
+        if f[0] == "op":
+            out.append(["op", f[1], f[2].split(",") if f[2] else [], [int(x) for x in f[3].split(",")] if f[3] else []])
+        else:
+            out.append(["copy", f[1], f[2], int(f[3]), int(f[4])])
+    return out
+
+
 def greedy(logits) -> int:
     logits = np.ascontiguousarray(logits, np.float32)
     return int(lib().tho_greedy(_f32(logits), logits.size))

@@ -17,6 +17,9 @@ tk_llama_token llama_sample_top_p_top_k(std::shared_ptr<LlamaModel> m,
         const std::vector<tk_llama_token>& last_n_tokens, int top_k, float top_p, float temp,
         float repeat_penalty, std::vector<float>& logits);
 std::vector<tk_llama_token> tk_llama_tokenize(std::shared_ptr<LlamaModel> m, const std::string& text, bool add_bos);
+// declared at th-llama.cpp:28-33, defined :464
+tk_llama_token th_eval_gpu(WGPUDevice device, WGPUQueue queue, std::shared_ptr<LlamaModel> m, const tk_llama_token* tokens,
+                           int n_tokens, int n_past);
 }
 
 struct RefModel { std::shared_ptr<th::LlamaModel> m; };
@@ -123,5 +126,59 @@ int ref_sample(int n_vocab, const float* logits, const int32_t* last_n, int n_la
 }
 
 uint64_t ref_dispatch_count(void) { return thstub_dispatch_count(); }
+
+// Run the reference's own th_eval_gpu (th-llama.cpp:464-660) on the stub and return the command stream it encoded:
+// a JSON document {"buffers": {id: name}, "commands": [...]}.  The logits are whatever the stub buffers hold (zeros:
+// no shader runs) -- only the ENCODING is observed.  The returned pointer is valid until the next call.
+const char* ref_trace_eval(void* h, const int32_t* tokens, int n_tokens, int n_past) {
+    static std::string out;
+    auto& m = ((RefModel*)h)->m;
+    std::string names = "{";
+    auto collect = [&]() {
+    auto add = [&](const std::string& name, th::TensorBuffer& t) {
+        if (!t.gpu) return;
+        const std::string key = "\"" + std::to_string(thstub_buffer_id(t.gpu)) + "\": ";
+        if (names.find(key) != std::string::npos) return;
+        if (names.size() > 1) names += ", ";
+        names += key + "\"" + name + "\"";
+    };
+    add("tok_embeddings", m->tok_embeddings); add("norm", m->norm); add("output", m->outputMat);
+    add("output-split1", m->outputMatSplit1); add("output-split2", m->outputMatSplit2);
+    add("out", m->out); add("outScratch", m->outScratch); add("resultBuffer", m->resultBuffer);
+    for (int i = 0; i < th::LlamaModel::nInpBuffers; ++i) add("inp" + std::to_string(i), m->inp[i]);
+    for (int i = 0; i < th::LlamaModel::nSplitScratch; ++i) add("splitScratch" + std::to_string(i), m->splitScratch[i]);
+    add("ffWorking0", m->ffWorking[0]); add("ffWorking1", m->ffWorking[1]);
+    add("working_key_cache", m->working_key_cache); add("working_val_cache", m->working_val_cache);
+    if (m->networkUniforms) {
+        const std::string key = "\"" + std::to_string(thstub_buffer_id(m->networkUniforms)) + "\": ";
+        if (names.find(key) == std::string::npos) { if (names.size() > 1) names += ", "; names += key + "\"networkUniforms\""; }
+    }
+    for (size_t l = 0; l < m->layers.size(); ++l) {
+        th::LlamaLayer& L = m->layers[l];
+        const std::string p = "layers." + std::to_string(l) + ".";
+        add(p + "attention_norm", L.attention_norm); add(p + "wq", L.wq); add(p + "wk", L.wk); add(p + "wv", L.wv);
+        add(p + "wo", L.wo); add(p + "ffn_norm", L.ffn_norm); add(p + "w1", L.w1); add(p + "w2", L.w2); add(p + "w3", L.w3);
+        add(p + "key_cache", L.key_cache); add(p + "value_cache", L.value_cache);
+    }
+    };
+    collect();
+    thstub_trace_begin();
+    std::vector<th::tk_llama_token> toks(tokens, tokens + n_tokens);
+    th::th_eval_gpu(thstub_device(), thstub_queue(), m, toks.data(), n_tokens, n_past);
+    std::string lines = thstub_trace_end();
+    collect();                      // th_eval_gpu re-creates m->out (th-llama.cpp): name the buffers that exist now as well
+    names += "}";
+    out = "{\"buffers\": " + names + ", \"commands\": [";
+    size_t pos = 0;
+    bool first = true;
+    while (pos < lines.size()) {
+        size_t nl = lines.find('\n', pos);
+        if (nl == std::string::npos) nl = lines.size();
+        if (nl > pos) { if (!first) out += ", "; out += lines.substr(pos, nl - pos); first = false; }
+        pos = nl + 1;
+    }
+    out += "]}";
+    return out.c_str();
+}
 
 }  // extern "C"

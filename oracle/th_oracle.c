@@ -14,6 +14,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stdarg.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -541,6 +542,35 @@ void tho_model_fill_kv_synthetic(tho_model* m, uint64_t seed, int n_positions) {
  * Buffer roles: inp0 = x (normed in place), inp6 = residual copy, inp1..3 = Q/K/V,
  * inp4 = Q^T, inp5 = scores.
  * ---------------------------------------------------------------------------------------- */
+/* Op trace (test infrastructure for tests/test_graph_trace.py): while a trace is open, eval_one logs every op it issues --
+ * the reference pipeline label, the reference names of the operand buffers and the words the reference puts into the op's
+ * uniform block -- so that the restated graph can be compared, command by command, with the stream the reference's own
+ * th_eval_gpu encodes on the WebGPU stub (tests/golden/graph_trace_tiny.json).  One line per command:
+ *   op|<label>|<operand>,<operand>,...|<uniform word>,...        copy|<src>|<dst>|<dst byte offset>|<bytes>          */
+static char* g_trace = NULL;
+static size_t g_trace_len = 0, g_trace_cap = 0;
+static int g_trace_on = 0;
+void tho_trace_begin(void) { g_trace_len = 0; if (g_trace) g_trace[0] = 0; g_trace_on = 1; }
+const char* tho_trace_end(void) { g_trace_on = 0; return g_trace ? g_trace : ""; }
+static void TR(const char* fmt, ...) {
+    if (!g_trace_on) return;
+    char line[256];
+    va_list ap;
+    va_start(ap, fmt);
+    const int n = vsnprintf(line, sizeof line, fmt, ap);
+    va_end(ap);
+    if (n <= 0) return;
+    if (g_trace_len + (size_t)n + 2 > g_trace_cap) {
+        g_trace_cap = (g_trace_cap + (size_t)n + 2) * 2;
+        g_trace = (char*)realloc(g_trace, g_trace_cap);
+    }
+    memcpy(g_trace + g_trace_len, line, (size_t)n);
+    g_trace_len += (size_t)n;
+    g_trace[g_trace_len++] = '\n';
+    g_trace[g_trace_len] = 0;
+}
+static uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
 static void matvec_t(const tho_tensor* W, const float* x, float* y) {
     if (W->ftype == THO_F16) tho_vector_mat_mul_trans_f16(x, (const uint16_t*)W->data, y, W->rows, W->cols, 1);
     else tho_vector_mat_mul_trans_f32(x, (const float*)W->data, y, W->rows, W->cols, 1);
@@ -562,45 +592,80 @@ static int eval_one(tho_model* m, int32_t token, int n_past, float* logits_out, 
         memcpy(inp0, (const float*)m->tok_embeddings.data + (int64_t)token * E, E * sizeof(float));
     memcpy(inp6, inp0, E * sizeof(float));
 
+    const long long Eb = (long long)(E * (int64_t)sizeof(float));
+    const float att_scale = 1.0f / sqrtf((float)D);
     for (int l = 0; l < m->hp.n_layer; ++l) {
         const tho_tensor* T = &m->layers[l * T_PER_LAYER];
         float* kc = m->key_cache[l];
         float* vc = m->value_cache[l];
         tho_rms_norm(inp0, 1, E);                                              /* :299 */
+        TR("op|rms_norm|inp0|");
         tho_row_element_multiply(inp0, (const float*)T[T_ATTN_NORM].data, 1, E); /* :300 */
+        TR("op|row_element_multiply|inp0,layers.%d.attention_norm|", l);
         matvec_t(&T[T_WQ], inp0, q);                                           /* :304 */
+        TR("op|vector_mat_mul|inp0,layers.%d.wq,inp1|", l);
         matvec_t(&T[T_WK], inp0, k);                                           /* :305 */
+        TR("op|vector_mat_mul|inp0,layers.%d.wk,inp2|", l);
         matvec_t(&T[T_WV], inp0, v);                                           /* :306 */
+        TR("op|vector_mat_mul|inp0,layers.%d.wv,inp3|", l);
         tho_rope(q, 1, H, D, (uint32_t)n_past);                                /* :321 */
+        TR("op|RoPE|inp1|%d,1", n_past);
         tho_rope(k, 1, H, D, (uint32_t)n_past);                                /* :322 */
+        TR("op|RoPE|inp2|%d,1", n_past);
         memcpy(kc + (int64_t)n_past * E, k, E * sizeof(float));                /* :337 */
+        TR("copy|inp2|layers.%d.key_cache|%lld|%lld", l, (long long)n_past * Eb, Eb);
         memcpy(vc + (int64_t)n_past * E, v, E * sizeof(float));                /* :338 */
+        TR("copy|inp3|layers.%d.value_cache|%lld|%lld", l, (long long)n_past * Eb, Eb);
         tho_transpose(kc, m->work_k, N, H, D, 1);                              /* :353 [N,H,D]->[H,N,D] */
+        TR("op|transpose|layers.%d.key_cache,working_key_cache|%lld,%lld,%lld", l, (long long)N, (long long)H, (long long)D);
         tho_transpose(vc, m->work_v, N, H, D, 1);                              /* :354 */
+        TR("op|transpose|layers.%d.value_cache,working_val_cache|%lld,%lld,%lld", l, (long long)N, (long long)H, (long long)D);
         tho_transpose(q, qT, 1, H, D, 1);                                      /* :355 */
-        tho_mat_mul(qT, m->work_k, scores, H, 1, D, N, 1, 1, 1.0f / sqrtf((float)D), 0); /* :365 */
+        TR("op|transpose|inp1,inp4|1,%lld,%lld", (long long)H, (long long)D);
+        tho_mat_mul(qT, m->work_k, scores, H, 1, D, N, 1, 1, att_scale, 0);    /* :365 */
+        TR("op|mat_mul|inp4,working_key_cache,inp5|%lld,1,%lld,%u,%lld,%lld,%lld", (long long)H, (long long)D, f32_bits(att_scale),
+           (long long)H, (long long)D, (long long)N);
         tho_row_softmax(scores, H, 1, N);                                      /* :373 */
+        TR("op|row_softmax|inp5|%lld,1,%lld", (long long)H, (long long)N);
         tho_mat_mul(scores, m->work_v, k, H, 1, N, D, 0, 1, 1.0f, 0);          /* :380 -> keyBuf */
+        TR("op|mat_mul|inp5,working_val_cache,inp2|%lld,1,%lld,%u,%lld,%lld,%lld", (long long)H, (long long)N, f32_bits(1.0f),
+           (long long)H, (long long)N, (long long)D);
         tho_transpose(k, v, H, 1, D, 1);                                       /* :397 -> valueBuf */
+        TR("op|transpose|inp2,inp3|");
         matvec_t(&T[T_WO], v, q);                                              /* :402 inp1 = Wo*ctx */
+        TR("op|vector_mat_mul|inp3,layers.%d.wo,inp1|", l);
         tho_addition(q, inp6, k, E);                                           /* :409 inp2 = inp1+inp6 */
+        TR("op|addition|inp1,inp6,inp2|");
         memcpy(v, k, E * sizeof(float));                                       /* :412 inp3 = inp2 */
+        TR("copy|inp2|inp3|0|%lld", Eb);
         tho_rms_norm(k, 1, E);                                                 /* :415 */
+        TR("op|rms_norm|inp2|");
         tho_row_element_multiply(k, (const float*)T[T_FFN_NORM].data, 1, E);   /* :416 */
+        TR("op|row_element_multiply|inp2,layers.%d.ffn_norm|", l);
         matvec_t(&T[T_W1], k, m->ff[0]);                                       /* :423 */
+        TR("op|vector_mat_mul|inp2,layers.%d.w1,ffWorking0|", l);
         matvec_t(&T[T_W3], k, m->ff[1]);                                       /* :424 */
+        TR("op|vector_mat_mul|inp2,layers.%d.w3,ffWorking1|", l);
         tho_silu(m->ff[0], F);                                                 /* :436 */
+        TR("op|silu|ffWorking0|");
         tho_element_mult_in_place(m->ff[0], m->ff[1], F);                      /* :438 */
+        TR("op|hadamard_in_place|ffWorking0,ffWorking1|");
         matvec_t(&T[T_W2], m->ff[0], k);                                       /* :441 */
+        TR("op|vector_mat_mul|ffWorking0,layers.%d.w2,inp2|", l);
         tho_addition(v, k, inp0, E);                                           /* :447 */
+        TR("op|addition|inp3,inp2,inp0|");
         memcpy(inp6, inp0, E * sizeof(float));                                 /* :450 */
+        TR("copy|inp0|inp6|0|%lld", Eb);
         if (hidden_out) memcpy(hidden_out + (int64_t)l * E, inp0, E * sizeof(float));
     }
     tho_rms_norm(inp0, 1, E);                                                  /* :252 */
+    TR("op|rms_norm|inp0|");
     tho_row_element_multiply(inp0, (const float*)m->norm.data, 1, E);          /* :253 */
+    TR("op|row_element_multiply|inp0,norm|");
     if (hidden_out) memcpy(hidden_out + (int64_t)m->hp.n_layer * E, inp0, E * sizeof(float));
     /* :255-262 split matvec + reduce; intended result = full dot product */
     matvec_t(&m->output, inp0, m->out);
+    TR("op|output_matvec|inp0,output,out|");          /* = the reference's two vector_mat_mul_split + vector_reduce */
     if (logits_out) memcpy(logits_out, m->out, (size_t)m->hp.n_vocab * sizeof(float));
     return 0;
 }

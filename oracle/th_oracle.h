@@ -109,6 +109,11 @@ float*     tho_model_value_cache(tho_model* m, int layer);
  * hidden_out (optional, n_layer+1 rows of n_embd) receives the residual stream after each
  * layer and, in the last row, the final normed vector.
  */
+/* Op trace of tho_eval (test infrastructure, tests/test_graph_trace.py): one line per command, reference labels and buffer
+ * names; see th_oracle.c.  Not thread safe. */
+void tho_trace_begin(void);
+const char* tho_trace_end(void);
+
 int tho_eval(tho_model* m, const int32_t* tokens, int n_tokens, int n_past,
              float* logits_out, float* hidden_out);
 

@@ -5,7 +5,8 @@
  * can be compiled, unmodified and from where they lie under /root/reference, into
  * oracle/_ref/libthref_host.so.  Buffers are plain host allocations; compute dispatches do
  * nothing (the WGSL cannot run here), so only the reference's HOST logic becomes executable:
- * fp16 helpers, sampler, tokenizer and the ggjt loader.
+ * fp16 helpers, sampler, tokenizer, the ggjt loader -- and th_eval_gpu's command encoding, which the
+ * stub can record (thstub_trace_begin / _end).
  */
 #ifndef TH_ORACLE_WEBGPU_STUB_H
 #define TH_ORACLE_WEBGPU_STUB_H
@@ -100,6 +101,9 @@ uint64_t thstub_buffer_size(WGPUBuffer);
 WGPUDevice thstub_device(void);
 WGPUQueue thstub_queue(void);
 uint64_t thstub_dispatch_count(void);
+uint32_t thstub_buffer_id(WGPUBuffer);
+void thstub_trace_begin(void);          /* start recording dispatches / copies / writes / submits */
+const char* thstub_trace_end(void);     /* stop; one JSON object per line, valid until the next begin */
 
 #ifdef __cplusplus
 }

@@ -107,6 +107,21 @@ def kernels() -> C.CDLL:
     return _k
 
 
+def trace_commands(fn):
+    """Test hook: run fn() and return the labels of the commands the host library issued through the reference's op
+    surface (cmdbuf_* names, "copy" for build_layer_cmdbuf's buffer-to-buffer copies)."""
+    H = host()
+    H.capi_trace_begin()
+    buf = C.create_string_buffer(1 << 20)
+    try:
+        fn()
+    finally:
+        n = H.capi_trace_end(buf, len(buf))
+    labels = buf.value.decode().splitlines()
+    assert n == len(labels), (n, len(labels))
+    return labels
+
+
 def host() -> C.CDLL:
     """libth_b200.so (host C++ layer)."""
     global _h
@@ -152,6 +167,9 @@ def host() -> C.CDLL:
         H.capi_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.c_int]
         H.capi_tune.argtypes = [vp, C.c_char_p, C.c_int]
         H.capi_hidden.argtypes = [vp, f32p]
+        H.capi_trace_begin.restype = None
+        H.capi_trace_begin.argtypes = []
+        H.capi_trace_end.argtypes = [C.c_char_p, C.c_int]
         H.capi_tensor_info.restype = i64
         H.capi_tensor_info.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
         H.capi_tensor_download.argtypes = [vp, C.c_char_p, vp, i64]

@@ -4,19 +4,21 @@
 // + build_final_compute_cmdbuf, th-llama.cpp:270-452, 240-268, 592-640) with a single launch of
 // one CTA per SM.  Design (DESIGN.md has the full write-up and the measurements behind it):
 //
-//   * 19 warps: warp 0 = PRODUCER, warp 1 = EPILOGUE, warp 2 = REDUCER (tensor parallel only), 16 MATH warps
-//     (four per SM sub-partition: a ready tile's wait / load / convert / FMA chain of one warp hides behind the other three).
+//   * 12 warps in three warpgroups.  Warps 0-7 = MATH (216 registers each, setmaxnreg.inc); warp 8 = PRODUCER, warp 9 =
+//     EPILOGUE, warp 10 = exchange REDUCER (tensor parallel only), warp 11 idle (72 registers each, setmaxnreg.dec).
+//     Nothing is out of line: one __noinline__ call caps every thread at the ABI's register budget (measured).
 //   * the PRODUCER walks the CTA's static list of weight / KV tiles for the whole token (all layers, all phases) and
-//     streams them HBM -> shared memory with cp.async.bulk (UBLKCP) into a ring of 32 KB slots guarded by full/empty
-//     mbarriers.  It never waits for activations, so HBM stays busy across phase boundaries; when a phase boundary stalls
-//     the ring it asks L2 for the CTA's next rows (UBLKPF).
-//   * a tile is 8 rows x <= 2048 columns of f16.  Math warp (chunk c, row half h) owns rows 4h..4h+3 of the 256-column
-//     chunk c: four 128-bit shared loads by shared-window address, exact f16 -> f32 conversion, packed FFMA2 against the
-//     activation values of its 8 columns -- held in REGISTERS for the whole phase when the phase has <= 2 K tiles (every
+//     streams them HBM -> shared memory with cp.async.bulk (UBLKCP) into a ring of four 32 KB slots guarded by full/empty
+//     mbarriers, L2 evict-first.  It never waits for activations, so HBM stays busy across phase boundaries; when a phase
+//     boundary stalls the ring it asks L2 for the CTA's next rows (UBLKPF).
+//   * a tile is 8 rows x <= 2048 columns of f16.  Math warp c owns the 8 rows of the 256-column chunk c: eight 128-bit
+//     shared loads by shared-window address, exact f16 -> f32 conversion (HADD2.F32), packed FFMA2 against the activation
+//     values of its 8 columns -- held in REGISTERS for the whole phase when the phase has <= 2 K tiles (every
 //     4096-column matrix), else re-read from shared memory.  The row sums of a finished row group are reduced with a
-//     transposing shuffle tree one tile LATER, between the next tile's loads and its math, and handed to the epilogue
-//     warp through a ring of records (mbarriers).
-//   * the EPILOGUE warp adds the sixteen warp sums per row in a fixed order and runs the fused epilogue (RMS scale, RoPE +
+//     transposing shuffle tree and handed to the epilogue warp through an 8-deep ring of records (mbarriers, ONE arrival
+//     per warp after __syncwarp: lanes diverge at per-lane try_wait predicates, and several lanes arriving on one
+//     mbarrier in the same instruction are not counted per lane).
+//   * the EPILOGUE warp adds the eight warp sums per row in a fixed order and runs the fused epilogue (RMS scale, RoPE +
 //     KV append, residual add, SiLU*mul, logits + argmax); it owns the grid barrier (one red.release + relaxed polling).
 //   * phases per layer: QKV | attention (split-KV, warp-private online softmax) | Wo | W1,W3 | W2; then logits.
 //     RMSNorm*gain is the prologue of the consuming phase; the split-KV combine is the prologue of Wo.  A grid barrier
@@ -28,7 +30,8 @@
 //     epoch-stamped vector locally -- so every math warp polls ONE 32 KB vector exactly as on a single GPU.
 //
 // Arithmetic follows oracle/th_oracle.c (the restatement of the WGSL); only summation order
-// differs.  No tensor cores: at M=1 the work is 1 FLOP/byte and HBM-bound.
+// differs.  No tensor cores: at M=1 the work is 1 FLOP/byte and HBM-bound.  What bounds the kernel today (the latency
+// chain of the 161 phase hand-offs, not the math) and everything that was tried: profiles/r2_timeline_and_experiments.md.
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>

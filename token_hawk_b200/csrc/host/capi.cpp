@@ -11,7 +11,7 @@
 
 using namespace th;
 
-namespace th { extern int64_t g_launch_count; }
+namespace th { extern int64_t g_launch_count; extern std::vector<std::string>* g_op_trace; }
 
 struct CapiModel { std::shared_ptr<LlamaModel> m; thk_ctx* ctx; };
 static thread_local std::string g_capi_err;
@@ -153,6 +153,23 @@ int capi_profile(void* h, int enable, unsigned long long* out, int n) {
     auto& m = ((CapiModel*)h)->m;
     return m->decoder ? thk_decoder_profile(m->decoder, enable, out, n) : -1;
 }
+// test hook: record the labels of the commands issued through the op surface (th.cpp: g_op_trace)
+void capi_trace_begin(void) {
+    static std::vector<std::string> trace;
+    trace.clear();
+    th::g_op_trace = &trace;
+}
+// -> number of commands; the labels, newline separated, into buf (truncated at cap)
+int capi_trace_end(char* buf, int cap) {
+    std::vector<std::string>* t = th::g_op_trace;
+    th::g_op_trace = nullptr;
+    if (!t) return -1;
+    std::string all;
+    for (const std::string& l : *t) { all += l; all += '\n'; }
+    if (buf && cap > 0) { const size_t n = all.size() < (size_t)cap - 1 ? all.size() : (size_t)cap - 1; memcpy(buf, all.data(), n); buf[n] = 0; }
+    return (int)t->size();
+}
+
 int capi_tune(void* h, const char* key, int value) {
     auto& m = ((CapiModel*)h)->m;
     return m->decoder ? thk_decoder_tune(m->decoder, key, value) : -1;

@@ -5,6 +5,8 @@
 
 #include <math.h>
 #include <string.h>
+#include <string>
+#include <vector>
 
 #include <chrono>
 
@@ -155,9 +157,15 @@ static int pipeline_gate(ComputePipeline* pipeline, bool checkShapes, const Tens
 // Without either, the reference hands back a finished command buffer for the caller to submit
 // (th.cpp:836-856); here that is a deferred launch executed by queue_submit().
 int64_t g_launch_count = 0;   // kernels launched through the op surface (bench's gpu_launches)
+// Test hook: while non-null, every command issued through the op surface appends its label (cmdbuf_* name, "copy" for
+// the buffer-to-buffer copies of build_layer_cmdbuf).  tests/test_gpu_graph_trace.py compares the sequence with the
+// command stream the reference's own th_eval_gpu encodes (tests/golden/graph_trace_tiny.json).
+std::vector<std::string>* g_op_trace = nullptr;
+void trace_command(const char* label) { if (g_op_trace) g_op_trace->push_back(label); }
 
 template <typename F>
 static CommandBuffer emit(WGPUCommandEncoder encoder, WGPUComputePassEncoder pass, const char* op, F launch) {
+    trace_command(op);
     if (!encoder && !pass) return CommandBuffer(std::function<int()>(launch), op);
     const int rc = launch();
     if (rc != THK_OK) { fprintf(stderr, "%s: %s\n", op, thk_last_error()); return {}; }

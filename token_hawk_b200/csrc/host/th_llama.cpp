@@ -18,6 +18,12 @@
 namespace th {
 
 extern int64_t g_launch_count;   // th.cpp: launches issued through emit()
+void trace_command(const char* label);   // th.cpp: test hook
+// wgpuCommandEncoderCopyBufferToBuffer of build_layer_cmdbuf (th-llama.cpp:337-338, :412, :450)
+static inline void copy_command(WGPUDevice device, void* dst, size_t dst_off, const void* src, size_t src_off, size_t bytes) {
+    trace_command("copy");
+    thk_copy(device, dst, dst_off, src, src_off, bytes);
+}
 
 static EncoderTag* const kEncoder = reinterpret_cast<EncoderTag*>(1);   // "a submission is open"
 
@@ -100,8 +106,8 @@ static void build_layer_cmdbuf_batch(WGPUDevice device, WGPUCommandEncoder encod
     cmdbuf_RoPE(device, encoder, nullptr, nullptr, queryBuf, m->networkUniforms);
     cmdbuf_RoPE(device, encoder, nullptr, nullptr, keyBuf, m->networkUniforms);
     const size_t off = (size_t)n_past * n_embd * sizeof(float), bytes = (size_t)T * n_embd * sizeof(float);
-    thk_copy(device, l.key_cache.gpu, off, keyBuf.gpu, 0, bytes);                                // :337-338
-    thk_copy(device, l.value_cache.gpu, off, valueBuf.gpu, 0, bytes);
+    copy_command(device, l.key_cache.gpu, off, keyBuf.gpu, 0, bytes);                                // :337-338
+    copy_command(device, l.value_cache.gpu, off, valueBuf.gpu, 0, bytes);
 
     l.key_cache.shape.b = N;
     l.value_cache.shape.b = N;
@@ -126,7 +132,7 @@ static void build_layer_cmdbuf_batch(WGPUDevice device, WGPUCommandEncoder encod
     cmdbuf_mat_mul(device, encoder, nullptr, nullptr, valueBuf, l.wo, m->inp[1], 1);             // :404
     m->inp[6].shape = rows; m->inp[2].shape = rows; m->inp[3].shape = rows;
     cmdbuf_addition(device, encoder, nullptr, nullptr, m->inp[1], m->inp[6], m->inp[2]);
-    thk_copy(device, m->inp[3].gpu, 0, m->inp[2].gpu, 0, bytes);
+    copy_command(device, m->inp[3].gpu, 0, m->inp[2].gpu, 0, bytes);
     cmdbuf_rms_norm(device, encoder, nullptr, nullptr, m->inp[2]);
     cmdbuf_row_element_multiply(device, encoder, nullptr, nullptr, m->inp[2], l.ffn_norm);
 
@@ -142,7 +148,7 @@ static void build_layer_cmdbuf_batch(WGPUDevice device, WGPUCommandEncoder encod
     cmdbuf_mat_mul(device, encoder, nullptr, nullptr, m->ffWorking[0], l.w2, m->inp[2], 1);
     m->inp[0].shape = rows;
     cmdbuf_addition(device, encoder, nullptr, nullptr, m->inp[3], m->inp[2], m->inp[0]);
-    thk_copy(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, bytes);
+    copy_command(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, bytes);
     reset_layer_tensors(l);
 }
 
@@ -176,8 +182,8 @@ void build_layer_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, std::shar
 
     if (encoder) {   // KV append, :332-339
         const size_t off = (size_t)n_past * n_embd * sizeof(float);
-        thk_copy(device, l.key_cache.gpu, off, keyBuf.gpu, 0, keyBuf.get_size_bytes());
-        thk_copy(device, l.value_cache.gpu, off, valueBuf.gpu, 0, valueBuf.get_size_bytes());
+        copy_command(device, l.key_cache.gpu, off, keyBuf.gpu, 0, keyBuf.get_size_bytes());
+        copy_command(device, l.value_cache.gpu, off, valueBuf.gpu, 0, valueBuf.get_size_bytes());
     }
 
     l.key_cache.shape.b = n_past + n_tokens;                                                        // :341-350
@@ -211,7 +217,7 @@ void build_layer_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, std::shar
     m->inp[6].shape = m->inp[1].shape;
     m->inp[2].shape = m->inp[1].shape;
     cmdbuf_addition(device, encoder, nullptr, &p.p11_add, m->inp[1], m->inp[6], m->inp[2]);         // :409
-    if (encoder) thk_copy(device, m->inp[3].gpu, 0, m->inp[2].gpu, 0, m->inp[2].get_size_bytes());  // :412
+    if (encoder) copy_command(device, m->inp[3].gpu, 0, m->inp[2].gpu, 0, m->inp[2].get_size_bytes());  // :412
 
     cmdbuf_rms_norm(device, encoder, nullptr, &p.p12_rms, m->inp[2]);                               // :415
     cmdbuf_row_element_multiply(device, encoder, nullptr, &p.p13_norm, m->inp[2], l.ffn_norm);      // :416
@@ -227,7 +233,7 @@ void build_layer_cmdbuf(WGPUDevice device, WGPUCommandEncoder encoder, std::shar
     m->inp[3].shape = m->inp[2].shape;
     m->inp[0].shape = m->inp[2].shape;
     cmdbuf_addition(device, encoder, nullptr, &p.p18_add, m->inp[3], m->inp[2], m->inp[0]);         // :447
-    if (encoder) thk_copy(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, m->inp[0].get_size_bytes());  // :450
+    if (encoder) copy_command(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, m->inp[0].get_size_bytes());  // :450
 }
 
 // greedy branch of th-llama.cpp:814-838; other temperatures are outside the hot path
@@ -405,7 +411,7 @@ static bool eval_one_opgraph(WGPUDevice device, WGPUQueue queue, std::shared_ptr
     CommandBuffer cb = cmdbuf_f16_f32_conversion(device, kEncoder, nullptr, nullptr, m->inp[0], emb, 4, 0, (int)(stride * token));
     emb.shape = keep;
     if (!cb.is_valid()) return false;
-    thk_copy(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, m->inp[0].get_size_bytes());
+    copy_command(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, m->inp[0].get_size_bytes());    // :573
     for (auto& l : m->layers) build_layer_cmdbuf(device, kEncoder, m, l, m->ps, 1, n_past);   // :596-618
     reset_working_memory_tensors(*m);
     build_final_compute_cmdbuf(device, kEncoder, m, m->pfs, 1);                               // :632
@@ -430,7 +436,7 @@ static bool eval_batch_opgraph(WGPUDevice device, WGPUQueue queue, std::shared_p
     }
     emb.shape = keep;
     if (!ok) return false;
-    thk_copy(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, (size_t)T * m->n_embd * sizeof(float));
+    copy_command(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, (size_t)T * m->n_embd * sizeof(float));   // :573
     const int64_t H = m->n_head, D = m->n_embd / m->n_head;
     for (auto& l : m->layers) {
         build_layer_cmdbuf(device, kEncoder, m, l, m->pb, T, n_past);

@@ -31,7 +31,7 @@ struct LlamaLayer {            // th-llama.hpp:37-55
     TensorBuffer w1{}, w2{}, w3{};
     TensorBuffer key_cache{};      // [n_ctx][n_head][head_dim] f32 -- op-graph path (reference layout)
     TensorBuffer value_cache{};
-    TensorBuffer key_cache_hpd{};  // [n_head][n_ctx][head_dim] f32 -- fused path (no per-token transposes)
+    TensorBuffer key_cache_hpd{};  // [n_head][n_ctx][head_dim] f32 (f16 when LlamaModel::kvF16) -- fused path (no per-token transposes)
     TensorBuffer value_cache_hpd{};
 };
 
@@ -98,6 +98,10 @@ struct LlamaModel {                  // th-llama.hpp:100-177
     // the op graph, [head][pos][dim] for the fused kernel).  Number of leading positions valid in each; th_eval_gpu
     // copies the missing rows across before it evaluates, so the paths can be mixed freely within one context.
     int32_t kvValidPhd = 0, kvValidHpd = 0;
+    // f16 KV for the fused path (no reference analogue -- the reference's cache is f32, th-llama-loader.cpp:335):
+    // the [head][pos][dim] cache holds f16, K (after RoPE) and V rounded to nearest-even when appended.  The op graph's
+    // [pos][head][dim] cache stays f32; rows crossing between the layouts are rounded / widened (thk_kv_*_hpd_f16).
+    bool kvF16 = false;
     float samplerTemp = 0.0f;        // reference hard-codes 0.8 (th-llama.cpp:721); greedy is the parity mode
     thk_decoder* decoder = nullptr;
     int32_t* d_token = nullptr;      // device: token id in, greedy id out

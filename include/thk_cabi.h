@@ -127,6 +127,12 @@ int thk_kv_to_hpd(thk_ctx* ctx, const float* src_phd, float* dst_hpd, int64_t po
 /* ... and back, so that the op graph / a batched pass can continue a context the fused decoder extended (one
  * authoritative cache per position: th_eval_gpu tracks which layout holds which rows) */
 int thk_kv_from_hpd(thk_ctx* ctx, const float* src_hpd, float* dst_phd, int64_t pos0, int64_t npos, int64_t n_ctx, int64_t H, int64_t D);
+/* the same two copies for an f16 fused-layout cache (thk_llama_dims.kv_f16): f32 rows are rounded to nearest-even on the way in,
+ * widened exactly on the way out */
+int thk_kv_to_hpd_f16(thk_ctx* ctx, const float* src_phd, uint16_t* dst_hpd, int64_t pos0, int64_t npos, int64_t n_ctx, int64_t H, int64_t D);
+int thk_kv_from_hpd_f16(thk_ctx* ctx, const uint16_t* src_hpd, float* dst_phd, int64_t pos0, int64_t npos, int64_t n_ctx, int64_t H, int64_t D);
+/* dst[i] = f16(src[i]), round to nearest even (no reference analogue: the reference only widens, th.cpp:4130-4200) */
+int thk_f32_to_f16(thk_ctx* ctx, const float* src, uint16_t* dst, int64_t n);
 
 /* ---- synthetic tensors (no reference analogue): same counter PRNG as the oracle ---- */
 int thk_fill_f16(thk_ctx* ctx, uint16_t* dst, uint64_t seed, uint64_t tensor_id, int64_t rows, int64_t cols,
@@ -143,6 +149,8 @@ int thk_fill_kv(thk_ctx* ctx, float* dst, uint64_t seed, uint64_t tensor_id, int
 typedef struct {
     int32_t n_vocab, n_embd, n_head, n_layer, n_ff, n_ctx;
     int32_t tp_rank, tp_size;   /* tensor parallel: this device owns heads/ff rows/vocab rows of rank */
+    int32_t kv_f16;             /* 0: f32 KV cache (the reference's, th-llama-loader.cpp:335-339); 1: the fused layout holds f16,
+                                 * K (after RoPE) and V rounded to nearest-even when appended -- half the KV bytes per token */
 } thk_llama_dims;
 
 typedef struct {                /* LlamaLayer, th-llama.hpp:37-55 (device pointers, local shards) */
@@ -155,7 +163,7 @@ typedef struct {                /* LlamaLayer, th-llama.hpp:37-55 (device pointe
     const uint16_t* w1;               /* [n_ff/tp, n_embd] */
     const uint16_t* w2;               /* [n_embd, n_ff/tp] */
     const uint16_t* w3;               /* [n_ff/tp, n_embd] */
-    float*          key_cache;        /* [n_head/tp][n_ctx][head_dim] f32  (fused-path layout) */
+    float*          key_cache;        /* [n_head/tp][n_ctx][head_dim] f32, or f16 when dims.kv_f16 (fused-path layout) */
     float*          value_cache;
 } thk_llama_layer;
 

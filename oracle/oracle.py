@@ -232,6 +232,13 @@ class Model:
         buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(p)
         return np.frombuffer(buf, dtype=dt).reshape(r.value, c.value)
 
+    def set_kv_f16(self, on: bool = True):
+        """product option (not the reference's): K/V rounded to f16 when appended; twin of LlamaModel(kv_f16=True)"""
+        L = lib()
+        L.tho_model_set_kv_f16.restype = None
+        L.tho_model_set_kv_f16.argtypes = [C.c_void_p, C.c_int]
+        L.tho_model_set_kv_f16(self.h, 1 if on else 0)
+
     def reset(self):
         lib().tho_model_reset(self.h)
 

@@ -403,6 +403,7 @@ struct tho_model {
     float** value_cache;
     /* working buffers (post_load_init_model, th-llama-loader.cpp:330-363) */
     float *inp[7], *ff[2], *work_k, *work_v, *out;
+    int kv_f16;         /* NOT the reference's: K (after RoPE) and V are rounded to f16 when appended (product option) */
 };
 
 int32_t tho_n_ff(const tho_hparams* hp) {
@@ -493,6 +494,8 @@ int tho_model_ready(const tho_model* m) {
 float* tho_model_key_cache(tho_model* m, int layer) { return m->key_cache[layer]; }
 float* tho_model_value_cache(tho_model* m, int layer) { return m->value_cache[layer]; }
 
+void tho_model_set_kv_f16(tho_model* m, int on) { m->kv_f16 = on != 0; }
+
 void tho_model_reset(tho_model* m) {
     const size_t kv = (size_t)m->hp.n_ctx * m->hp.n_embd * sizeof(float);
     for (int l = 0; l < m->hp.n_layer; ++l) { memset(m->key_cache[l], 0, kv); memset(m->value_cache[l], 0, kv); }
@@ -533,6 +536,12 @@ void tho_model_fill_kv_synthetic(tho_model* m, uint64_t seed, int n_positions) {
     for (int l = 0; l < m->hp.n_layer; ++l) {
         tho_fill_kv(m->key_cache[l], seed, 1000 + 2ull * l, n);
         tho_fill_kv(m->value_cache[l], seed, 1001 + 2ull * l, n);
+        if (m->kv_f16) {
+            for (int64_t i = 0; i < n; ++i) {
+                m->key_cache[l][i] = tho_fp16_to_fp32(tho_fp32_to_fp16(m->key_cache[l][i]));
+                m->value_cache[l][i] = tho_fp16_to_fp32(tho_fp32_to_fp16(m->value_cache[l][i]));
+            }
+        }
     }
 }
 
@@ -612,6 +621,9 @@ static int eval_one(tho_model* m, int32_t token, int n_past, float* logits_out, 
         TR("op|RoPE|inp1|%d,1", n_past);
         tho_rope(k, 1, H, D, (uint32_t)n_past);                                /* :322 */
         TR("op|RoPE|inp2|%d,1", n_past);
+        if (m->kv_f16) {   /* product option: the cache holds f16 (round to nearest even); the f32 path below is the reference's */
+            for (int64_t i = 0; i < E; ++i) { k[i] = tho_fp16_to_fp32(tho_fp32_to_fp16(k[i])); v[i] = tho_fp16_to_fp32(tho_fp32_to_fp16(v[i])); }
+        }
         memcpy(kc + (int64_t)n_past * E, k, E * sizeof(float));                /* :337 */
         TR("copy|inp2|layers.%d.key_cache|%lld|%lld", l, (long long)n_past * Eb, Eb);
         memcpy(vc + (int64_t)n_past * E, v, E * sizeof(float));                /* :338 */

@@ -109,6 +109,11 @@ float*     tho_model_value_cache(tho_model* m, int layer);
  * hidden_out (optional, n_layer+1 rows of n_embd) receives the residual stream after each
  * layer and, in the last row, the final normed vector.
  */
+/* Product option, NOT the reference's (its cache is f32, th-llama-loader.cpp:335): round K (after RoPE) and V to f16, nearest
+ * even, when they are appended to the cache, and tho_model_fill_kv_synthetic's values likewise.  Oracle twin of
+ * thk_llama_dims.kv_f16. */
+void tho_model_set_kv_f16(tho_model* m, int on);
+
 /* Op trace of tho_eval (test infrastructure, tests/test_graph_trace.py): one line per command, reference labels and buffer
  * names; see th_oracle.c.  Not thread safe. */
 void tho_trace_begin(void);

@@ -11,7 +11,7 @@ import token_hawk_b200 as th
 
 
 class Dims(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_embd", "n_head", "n_layer", "n_ff", "n_ctx", "tp_rank", "tp_size")]
+    _fields_ = [(n, C.c_int32) for n in ("n_vocab", "n_embd", "n_head", "n_layer", "n_ff", "n_ctx", "tp_rank", "tp_size", "kv_f16")]
 
 
 def plan(dims, phase, grid, cta):

@@ -77,6 +77,9 @@ def kernels() -> C.CDLL:
             "thk_element_mult_in_place": [vp, vp, vp, i64],
             "thk_f16_f32_conversion": [vp, vp, C.c_size_t, vp, C.c_size_t, i64],
             "thk_kv_to_hpd": [vp, vp, vp, i64, i64, i64, i64, i64],
+            "thk_kv_to_hpd_f16": [vp, vp, vp, i64, i64, i64, i64, i64],
+            "thk_kv_from_hpd_f16": [vp, vp, vp, i64, i64, i64, i64, i64],
+            "thk_f32_to_f16": [vp, vp, vp, i64],
             "thk_fill_f16": [vp, vp, u64, u64, i64, i64, i64, i64, i64],
             "thk_fill_gain": [vp, vp, u64, u64, i64],
             "thk_fill_kv": [vp, vp, u64, u64, i64, i64, i64, i64, i64, i64],
@@ -167,6 +170,8 @@ def host() -> C.CDLL:
         H.capi_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.c_int]
         H.capi_tune.argtypes = [vp, C.c_char_p, C.c_int]
         H.capi_hidden.argtypes = [vp, f32p]
+        H.capi_set_default_kv_f16.restype = None
+        H.capi_set_default_kv_f16.argtypes = [C.c_int]
         H.capi_trace_begin.restype = None
         H.capi_trace_begin.argtypes = []
         H.capi_trace_end.argtypes = [C.c_char_p, C.c_int]
@@ -322,12 +327,22 @@ class LlamaModel:
 
     @classmethod
     def synthetic(cls, dev: Device, n_vocab=32000, n_embd=4096, n_mult=256, n_head=32, n_layer=32, n_ctx=512, seed=0x7B5EED,
-                  tp_rank=0, tp_size=1):
-        return cls(dev, host().capi_model_synthetic_tp(dev.h, n_vocab, n_embd, n_mult, n_head, n_layer, n_ctx, seed, tp_rank, tp_size))
+                  tp_rank=0, tp_size=1, kv_f16=False):
+        """kv_f16: the fused path keeps its KV cache in f16 (K after RoPE and V rounded to nearest-even at append): half the
+        KV bytes per token; parity is then against the oracle's kv_f16 mode (tests/test_gpu_kv_f16.py)."""
+        host().capi_set_default_kv_f16(1 if kv_f16 else 0)
+        try:
+            return cls(dev, host().capi_model_synthetic_tp(dev.h, n_vocab, n_embd, n_mult, n_head, n_layer, n_ctx, seed, tp_rank, tp_size))
+        finally:
+            host().capi_set_default_kv_f16(0)
 
     @classmethod
-    def load(cls, dev: Device, path: str, n_ctx: int = 512, tp_rank=0, tp_size=1):
-        return cls(dev, host().capi_model_load_tp(dev.h, path.encode(), n_ctx, tp_rank, tp_size))
+    def load(cls, dev: Device, path: str, n_ctx: int = 512, tp_rank=0, tp_size=1, kv_f16=False):
+        host().capi_set_default_kv_f16(1 if kv_f16 else 0)
+        try:
+            return cls(dev, host().capi_model_load_tp(dev.h, path.encode(), n_ctx, tp_rank, tp_size))
+        finally:
+            host().capi_set_default_kv_f16(0)
 
     # ---- tensor-parallel wiring (token_hawk_b200.tp) ----
     def exchange_info(self):

@@ -105,6 +105,7 @@ struct DecParams {
     float* next_logit;
     PhaseDesc ph[5];
     int att_tpos;                       // positions per attention tile
+    int kv_f16;                         // KV cache element type of the fused layout: 0 = f32 (reference), 1 = f16 (rounded at append)
     int att_max_split;
     unsigned long long timeout_ns;
     // tensor parallel exchange (tp_size > 1): every rank owns one region laid out as
@@ -539,11 +540,12 @@ __device__ __forceinline__ void produce_att_phase(const DecParams& p, const Smem
         if (pb > p.n_past) pb = p.n_past;            // position n_past is read from global by the consumers
         for (int pos = pa; pos < pb; pos += p.att_tpos) {
             const int np = min(p.att_tpos, pb - pos);
-            const uint32_t bytes = (uint32_t)np * D * 4u;
+            const uint32_t esz = p.kv_f16 ? 2u : 4u;
+            const uint32_t bytes = (uint32_t)np * D * esz;
             for (int kv = 0; kv < 2; ++kv) {
                 wait_empty(p, S, c, 2);
                 if (PROF(p) && first && lane == 0) { prof_mark(PROF(p), phase_idx, PROF_PROD_FIRST); first = false; }
-                const float* base = (kv == 0 ? L.key_cache : L.value_cache) + ((size_t)h * p.n_ctx + pos) * D;
+                const unsigned char* base = (const unsigned char*)(kv == 0 ? L.key_cache : L.value_cache) + ((size_t)h * p.n_ctx + pos) * D * esz;
                 const uint32_t fb = S.full_a + c.ring.sl * 8;
                 if (lane == 0 && !c.dead) { mbar_expect_tx(fb, bytes); bulk_g2s(S.slots_a + c.ring.sl * kSlotBytes, base, bytes, fb, c.pol); }
                 __syncwarp();
@@ -842,6 +844,14 @@ __device__ __forceinline__ float wait_flagged1(const DecParams& p, const unsigne
 // softmax over the positions j = warp (mod 8) of each K/V tile pair -- no CTA barrier per tile -- and
 // the 8 warps are merged once per unit.  The split results {m, l, o[D]} go to p.part; the Wo
 // prologue merges the splits of a head.
+// this lane's 4 dims of KV row j of a tile (f32 or f16 rows)
+__device__ __forceinline__ float4 kv_row4(const void* tile, int j, int D, int lane, bool f16) {
+    if (!f16) return *(const float4*)((const float*)tile + j * D + (lane << 2));
+    const uint2 u = *(const uint2*)((const uint16_t*)tile + j * D + (lane << 2));
+    const float2 a = h2_to_f2(u.x), b = h2_to_f2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 __device__ __forceinline__ unsigned long long math_att_phase(const DecParams& p, unsigned long long state, int layer) {
     const Smem S = smem_view();
     const int ct = (int)threadIdx.x - kMathBase, mw = ct >> 5, lane = ct & 31;
@@ -853,6 +863,7 @@ __device__ __forceinline__ unsigned long long math_att_phase(const DecParams& p,
     const int D = p.head_dim;
     const float scale = 1.0f / sqrtf((float)D);
     const bool act = lane < (D >> 2);
+    const bool kvh = p.kv_f16 != 0;
     float* sc_o = S.red + kAttScratchOff;             // [8][128]
     float* sc_m = sc_o + kMathWarps * kMaxHeadDim;    // [8]
     float* sc_l = sc_m + kMathWarps;                  // [8]
@@ -869,8 +880,17 @@ __device__ __forceinline__ unsigned long long math_att_phase(const DecParams& p,
             q4 = __ldcg((const float4*)(p.q + h * D) + lane);
             if (has_new && mw == 0) {   // the token's own K/V row (QKV epilogue of this launch): same L2 round trip as q,
                 const size_t off = ((size_t)h * p.n_ctx + p.n_past) * D;     // parked in shared memory until the tiles are done
-                const float4 kn4 = __ldcg((const float4*)(L.key_cache + off) + lane);
-                const float4 vn4 = __ldcg((const float4*)(L.value_cache + off) + lane);
+                float4 kn4, vn4;
+                if (!kvh) {
+                    kn4 = __ldcg((const float4*)(L.key_cache + off) + lane);
+                    vn4 = __ldcg((const float4*)(L.value_cache + off) + lane);
+                } else {
+                    const uint2 ku = __ldcg((const uint2*)((const uint16_t*)L.key_cache + off) + lane);
+                    const uint2 vu = __ldcg((const uint2*)((const uint16_t*)L.value_cache + off) + lane);
+                    const float2 ka = h2_to_f2(ku.x), kb = h2_to_f2(ku.y), va = h2_to_f2(vu.x), vb = h2_to_f2(vu.y);
+                    kn4 = make_float4(ka.x, ka.y, kb.x, kb.y);
+                    vn4 = make_float4(va.x, va.y, vb.x, vb.y);
+                }
                 *(float4*)(sc_kn + (lane << 2)) = kn4;
                 *(float4*)(sc_vn + (lane << 2)) = vn4;
             }
@@ -881,18 +901,18 @@ __device__ __forceinline__ unsigned long long math_att_phase(const DecParams& p,
             const int np = min(p.att_tpos, pb - pos);
             // the K tile and the V tile of these positions sit in consecutive slots
             wait_full(p, S, c, 4);
-            const float* kt = (const float*)(S.slots + c.ring.sl * kSlotBytes);
+            const void* kt = (const void*)(S.slots + c.ring.sl * kSlotBytes);
             Cons cv = c;
             cv.ring.advance();
             wait_full(p, S, cv, 5);
-            const float* vt = (const float*)(S.slots + cv.ring.sl * kSlotBytes);
+            const void* vt = (const void*)(S.slots + cv.ring.sl * kSlotBytes);
             c.dead = c.dead || cv.dead;
             for (int j0 = mw; j0 < np; j0 += 4 * kMathWarps) {      // 4 positions of this warp per round
                 float s[4];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int j = j0 + t * kMathWarps;
-                    s[t] = (act && j < np) ? dot4(q4, *(const float4*)(kt + j * D + (lane << 2))) : 0.f;
+                    s[t] = (act && j < np) ? dot4(q4, kv_row4(kt, j, D, lane, kvh)) : 0.f;
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
@@ -913,7 +933,7 @@ __device__ __forceinline__ unsigned long long math_att_phase(const DecParams& p,
                         const float pj = expf(s[t] - m);
                         lsum += pj;
                         if (act) {
-                            const float4 v4 = *(const float4*)(vt + j * D + (lane << 2));
+                            const float4 v4 = kv_row4(vt, j, D, lane, kvh);
                             o4.x = fmaf(pj, v4.x, o4.x); o4.y = fmaf(pj, v4.y, o4.y);
                             o4.z = fmaf(pj, v4.z, o4.z); o4.w = fmaf(pj, v4.w, o4.w);
                         }
@@ -1266,12 +1286,18 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
                 switch (kind) {
                 case EPI_QKV:
                     if (si == 2) {                                   // V: append (th-llama.cpp:338)
-                        L->value_cache[((size_t)(r / D) * n_ctx + n_past) * D + (r % D)] = y;
+                        const size_t idx = ((size_t)(r / D) * n_ctx + n_past) * D + (r % D);
+                        if (!p.kv_f16) L->value_cache[idx] = y;
+                        else ((__half*)L->value_cache)[idx] = __float2half_rn(y);
                     } else if ((lane & 1) == 0) {                    // Q / K: rotate the pair (r, r+1), th.cpp:1457-1492
                         const float2 cs = S.misc->rope[(r % D) >> 1];
                         const float a = y * cs.x - y1 * cs.y, b = y * cs.y + y1 * cs.x;
                         if (si == 0) { *(float2*)(p.q + r) = make_float2(a, b); }
-                        else *(float2*)(L->key_cache + ((size_t)(r / D) * n_ctx + n_past) * D + (r % D)) = make_float2(a, b);   // th-llama.cpp:337
+                        else {                                                                            // th-llama.cpp:337
+                            const size_t idx = ((size_t)(r / D) * n_ctx + n_past) * D + (r % D);
+                            if (!p.kv_f16) *(float2*)(L->key_cache + idx) = make_float2(a, b);
+                            else *(__half2*)((__half*)L->key_cache + idx) = __floats2half2_rn(a, b);
+                        }
                     }
                     break;
                 case EPI_WO:                                                           // th-llama.cpp:409
@@ -1637,7 +1663,8 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
         for (int i = 0; i < 5; ++i)
             fprintf(stderr, "phase %d: C=%d CT=%d KT=%d rows=%d,%d,%d paired=%d\n", i, p.ph[i].C, p.ph[i].CT, p.ph[i].KT,
                     p.ph[i].rows[0], p.ph[i].rows[1], p.ph[i].rows[2], p.ph[i].paired);
-    p.att_tpos = kSlotBytes / (D * 4);
+    p.kv_f16 = dims->kv_f16 ? 1 : 0;
+    p.att_tpos = kSlotBytes / (D * (p.kv_f16 ? 2 : 4));
     if (p.att_tpos > kMaxTilePos) p.att_tpos = kMaxTilePos;
     p.att_max_split = d->grid / p.Hl > 0 ? d->grid / p.Hl : 1;
     if (p.att_max_split > kMaxSplit) p.att_max_split = kMaxSplit;

@@ -11,7 +11,7 @@
 
 using namespace th;
 
-namespace th { extern int64_t g_launch_count; extern std::vector<std::string>* g_op_trace; }
+namespace th { extern int64_t g_launch_count; extern std::vector<std::string>* g_op_trace; extern bool g_default_kv_f16; }
 
 struct CapiModel { std::shared_ptr<LlamaModel> m; thk_ctx* ctx; };
 static thread_local std::string g_capi_err;
@@ -153,6 +153,9 @@ int capi_profile(void* h, int enable, unsigned long long* out, int n) {
     auto& m = ((CapiModel*)h)->m;
     return m->decoder ? thk_decoder_profile(m->decoder, enable, out, n) : -1;
 }
+// models created after this call keep the fused path's KV cache in f16 (1) or f32 (0, the reference's)
+void capi_set_default_kv_f16(int on) { th::g_default_kv_f16 = on != 0; }
+
 // test hook: record the labels of the commands issued through the op surface (th.cpp: g_op_trace)
 void capi_trace_begin(void) {
     static std::vector<std::string> trace;

@@ -18,6 +18,18 @@
 namespace th {
 
 extern int64_t g_launch_count;   // th.cpp: launches issued through emit()
+// rows [pos0, pos0 + npos) between the op graph's f32 [pos][head][dim] cache and the fused kernel's [head][pos][dim] cache
+// (f32, or f16 when LlamaModel::kvF16: rounded on the way in, widened on the way out)
+static int kv_rows_to_hpd(const LlamaModel& m, const TensorBuffer& phd, const TensorBuffer& hpd, int64_t pos0, int64_t npos) {
+    const int64_t H = m.n_head, D = m.n_embd / m.n_head;
+    return m.kvF16 ? thk_kv_to_hpd_f16(m.device, (const float*)phd.gpu, (uint16_t*)hpd.gpu, pos0, npos, m.n_ctx, H, D)
+                   : thk_kv_to_hpd(m.device, (const float*)phd.gpu, (float*)hpd.gpu, pos0, npos, m.n_ctx, H, D);
+}
+static int kv_rows_from_hpd(const LlamaModel& m, const TensorBuffer& hpd, const TensorBuffer& phd, int64_t pos0, int64_t npos) {
+    const int64_t H = m.n_head, D = m.n_embd / m.n_head;
+    return m.kvF16 ? thk_kv_from_hpd_f16(m.device, (const uint16_t*)hpd.gpu, (float*)phd.gpu, pos0, npos, m.n_ctx, H, D)
+                   : thk_kv_from_hpd(m.device, (const float*)hpd.gpu, (float*)phd.gpu, pos0, npos, m.n_ctx, H, D);
+}
 void trace_command(const char* label);   // th.cpp: test hook
 // wgpuCommandEncoderCopyBufferToBuffer of build_layer_cmdbuf (th-llama.cpp:337-338, :412, :450)
 static inline void copy_command(WGPUDevice device, void* dst, size_t dst_off, const void* src, size_t src_off, size_t bytes) {
@@ -437,11 +449,10 @@ static bool eval_batch_opgraph(WGPUDevice device, WGPUQueue queue, std::shared_p
     emb.shape = keep;
     if (!ok) return false;
     copy_command(device, m->inp[6].gpu, 0, m->inp[0].gpu, 0, (size_t)T * m->n_embd * sizeof(float));   // :573
-    const int64_t H = m->n_head, D = m->n_embd / m->n_head;
     for (auto& l : m->layers) {
         build_layer_cmdbuf(device, kEncoder, m, l, m->pb, T, n_past);
-        if (thk_kv_to_hpd(device, (const float*)l.key_cache.gpu, (float*)l.key_cache_hpd.gpu, n_past, T, m->n_ctx, H, D)) return false;
-        if (thk_kv_to_hpd(device, (const float*)l.value_cache.gpu, (float*)l.value_cache_hpd.gpu, n_past, T, m->n_ctx, H, D)) return false;
+        if (kv_rows_to_hpd(*m, l.key_cache, l.key_cache_hpd, n_past, T)) return false;
+        if (kv_rows_to_hpd(*m, l.value_cache, l.value_cache_hpd, n_past, T)) return false;
     }
     reset_working_memory_tensors(*m);
     LlamaFinalComputePipeline pf;                                     // uncached: shapes depend on the batch size
@@ -459,13 +470,12 @@ static bool kv_sync(std::shared_ptr<LlamaModel> m, bool want_hpd, int n_past, in
         const int32_t other = want_hpd ? m->kvValidPhd : m->kvValidHpd;
         if (have < n_past) {
             if (other < n_past) { fprintf(stderr, "th_eval_gpu: n_past %d but only %d positions were evaluated\n", n_past, std::max(have, other)); return false; }
-            const int64_t H = m->n_head, D = m->n_embd / m->n_head;
             for (auto& l : m->layers) {
                 const int rc = want_hpd
-                    ? (thk_kv_to_hpd(m->device, (const float*)l.key_cache.gpu, (float*)l.key_cache_hpd.gpu, have, n_past - have, m->n_ctx, H, D) ||
-                       thk_kv_to_hpd(m->device, (const float*)l.value_cache.gpu, (float*)l.value_cache_hpd.gpu, have, n_past - have, m->n_ctx, H, D))
-                    : (thk_kv_from_hpd(m->device, (const float*)l.key_cache_hpd.gpu, (float*)l.key_cache.gpu, have, n_past - have, m->n_ctx, H, D) ||
-                       thk_kv_from_hpd(m->device, (const float*)l.value_cache_hpd.gpu, (float*)l.value_cache.gpu, have, n_past - have, m->n_ctx, H, D));
+                    ? (kv_rows_to_hpd(*m, l.key_cache, l.key_cache_hpd, have, n_past - have) ||
+                       kv_rows_to_hpd(*m, l.value_cache, l.value_cache_hpd, have, n_past - have))
+                    : (kv_rows_from_hpd(*m, l.key_cache_hpd, l.key_cache, have, n_past - have) ||
+                       kv_rows_from_hpd(*m, l.value_cache_hpd, l.value_cache, have, n_past - have));
                 if (rc) { fprintf(stderr, "th_eval_gpu: %s\n", thk_last_error()); return false; }
             }
         }

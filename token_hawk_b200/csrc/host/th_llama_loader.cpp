@@ -12,6 +12,8 @@
 #include <fstream>
 
 namespace th {
+bool g_default_kv_f16 = false;   // models created from now on keep the fused path's KV cache in f16 (LlamaModel::kvF16)
+
 
 static const int32_t kftype_f32 = 0, kftype_f16 = 1;
 static const uint32_t ggmlMagicUnversioned = 0x67676d6c, ggmlMagicValue = 0x67676a74, llamaFileVersion = 1;
@@ -159,8 +161,8 @@ void post_load_init_model(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Ll
         l.w3 = take(m.get(), p + "feed_forward.w3.weight", TensorType_F16, Fh, E, ok, Shard_Rows);
         l.key_cache = TensorBuffer(kvShape, TensorType_F32, device);
         l.value_cache = TensorBuffer(kvShape, TensorType_F32, device);
-        l.key_cache_hpd = TensorBuffer(kvShapeHpd, TensorType_F32, device);
-        l.value_cache_hpd = TensorBuffer(kvShapeHpd, TensorType_F32, device);
+        l.key_cache_hpd = TensorBuffer(kvShapeHpd, m->kvF16 ? TensorType_F16 : TensorType_F32, device);
+        l.value_cache_hpd = TensorBuffer(kvShapeHpd, m->kvF16 ? TensorType_F16 : TensorType_F32, device);
         for (TensorBuffer* t : {&l.key_cache, &l.value_cache, &l.key_cache_hpd, &l.value_cache_hpd}) {
             if (!t->gpu) { ok = false; break; }
             thk_memset(device, t->gpu, 0, t->get_size_bytes());
@@ -203,6 +205,7 @@ void post_load_init_model(WGPUDevice device, WGPUQueue queue, std::shared_ptr<Ll
     thk_llama_dims dims{};
     dims.n_vocab = m->n_vocab; dims.n_embd = m->n_embd; dims.n_head = m->n_head; dims.n_layer = m->n_layer;
     dims.n_ff = m->n_ff; dims.n_ctx = m->n_ctx; dims.tp_rank = m->tp_rank; dims.tp_size = (int32_t)tp;
+    dims.kv_f16 = m->kvF16 ? 1 : 0;
     std::vector<thk_llama_layer> L(m->n_layer);
     for (int i = 0; i < m->n_layer; ++i) {
         const LlamaLayer& l = m->layers[i];
@@ -230,6 +233,7 @@ std::shared_ptr<LlamaModel> load_llama_file(WGPUDevice device, WGPUQueue queue, 
     const int64_t fileSize = (int64_t)fin.tellg();
     fin.seekg(0, std::ios::beg);
     auto m = std::make_shared<LlamaModel>();
+    m->kvF16 = g_default_kv_f16;
     m->n_ctx = n_ctx;
     m->tp_rank = tp_rank; m->tp_size = tp_size > 0 ? tp_size : 1;
     m->device = device;
@@ -296,6 +300,7 @@ std::shared_ptr<LlamaModel> create_synthetic_llama(WGPUDevice device, WGPUQueue 
                                                    int32_t n_head, int32_t n_layer, int32_t n_ctx, uint64_t seed, int32_t tp_rank,
                                                    int32_t tp_size) {
     auto m = std::make_shared<LlamaModel>();
+    m->kvF16 = g_default_kv_f16;
     m->tp_rank = tp_rank; m->tp_size = tp_size > 0 ? tp_size : 1;
     m->device = device;
     if (n_head % m->tp_size || n_vocab % m->tp_size) { fprintf(stderr, "create_synthetic_llama: tp_size must divide n_head and n_vocab\n"); return {}; }
@@ -347,15 +352,32 @@ std::shared_ptr<LlamaModel> create_synthetic_llama(WGPUDevice device, WGPUQueue 
 bool fill_kv_synthetic(std::shared_ptr<LlamaModel> m, uint64_t seed, int n_positions) {
     if (!m || n_positions < 1 || n_positions > m->n_ctx) return false;
     const int64_t H = m->n_head, D = m->n_embd / m->n_head, Hl = H / m->tp_size, h0 = m->tp_rank * Hl;
-    for (int l = 0; l < m->n_layer; ++l) {
-        LlamaLayer& L = m->layers[l];
-        // fused layout [head][pos][dim] (local heads only under tensor parallelism)
-        if (thk_fill_kv(m->device, (float*)L.key_cache_hpd.gpu, seed, 1000 + 2ull * l, n_positions, m->n_ctx, H, h0, Hl, D)) return false;
-        if (thk_fill_kv(m->device, (float*)L.value_cache_hpd.gpu, seed, 1001 + 2ull * l, n_positions, m->n_ctx, H, h0, Hl, D)) return false;
-        // reference layout [pos][head][dim] = transpose of the above (zy on [H][n_ctx][D])
-        if (thk_transpose(m->device, (const float*)L.key_cache_hpd.gpu, (float*)L.key_cache.gpu, Hl, m->n_ctx, D, 1, nullptr)) return false;
-        if (thk_transpose(m->device, (const float*)L.value_cache_hpd.gpu, (float*)L.value_cache.gpu, Hl, m->n_ctx, D, 1, nullptr)) return false;
+    float* tmp = nullptr;                        // f16 KV: the synthetic values are generated in f32 and rounded like an append would
+    if (m->kvF16) {
+        void* t = nullptr;
+        if (thk_malloc(m->device, (size_t)Hl * m->n_ctx * D * sizeof(float), &t) != THK_OK) return false;
+        tmp = (float*)t;
     }
+    bool ok = true;
+    for (int l = 0; l < m->n_layer && ok; ++l) {
+        LlamaLayer& L = m->layers[l];
+        for (int kv = 0; kv < 2 && ok; ++kv) {
+            TensorBuffer& hpd = kv == 0 ? L.key_cache_hpd : L.value_cache_hpd;
+            TensorBuffer& phd = kv == 0 ? L.key_cache : L.value_cache;
+            float* f32_hpd = m->kvF16 ? tmp : (float*)hpd.gpu;
+            // fused layout [head][pos][dim] (local heads only under tensor parallelism)
+            ok = ok && !thk_fill_kv(m->device, f32_hpd, seed, 1000 + 2ull * l + kv, n_positions, m->n_ctx, H, h0, Hl, D);
+            if (m->kvF16) {
+                const int64_t n = Hl * m->n_ctx * D;
+                ok = ok && !thk_f32_to_f16(m->device, f32_hpd, (uint16_t*)hpd.gpu, n);
+                ok = ok && !thk_f16_f32_conversion(m->device, f32_hpd, 0, (const uint16_t*)hpd.gpu, 0, n);   // the rounded values
+            }
+            // reference layout [pos][head][dim] = transpose of the above (zy on [H][n_ctx][D])
+            ok = ok && !thk_transpose(m->device, f32_hpd, (float*)phd.gpu, Hl, m->n_ctx, D, 1, nullptr);
+        }
+    }
+    if (tmp) { thk_sync(m->device); thk_free(m->device, tmp); }
+    if (!ok) return false;
     m->kvValidPhd = m->tp_size == 1 ? n_positions : 0;
     m->kvValidHpd = n_positions;
     return thk_sync(m->device) == THK_OK;

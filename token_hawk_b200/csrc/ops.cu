@@ -453,6 +453,51 @@ extern "C" int thk_kv_to_hpd(thk_ctx* ctx, const float* src_phd, float* dst_hpd,
     THK_LAUNCH_CHECK();
     return THK_OK;
 }
+// ... into an f16 fused-layout cache (thk_llama_dims.kv_f16): rounded to nearest even, like the fused kernel's own append
+__global__ void kv_to_hpd_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t pos0, int64_t npos, int64_t n_ctx,
+                                     int64_t H, int64_t D) {
+    const int64_t total = npos * H * D;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = i % D, h = (i / D) % H, pz = i / (D * H);
+        dst[(h * n_ctx + pos0 + pz) * D + d] = __float2half_rn(src[((pos0 + pz) * H + h) * D + d]);
+    }
+}
+extern "C" int thk_kv_to_hpd_f16(thk_ctx* ctx, const float* src_phd, uint16_t* dst_hpd, int64_t pos0, int64_t npos, int64_t n_ctx, int64_t H,
+                                 int64_t D) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx && src_phd && dst_hpd, "thk_kv_to_hpd_f16: null argument");
+    THK_CHECK_ARG(pos0 >= 0 && npos > 0 && pos0 + npos <= n_ctx && H > 0 && D > 0, "thk_kv_to_hpd_f16: bad range");
+    kv_to_hpd_f16_kernel<<<ew_blocks(ctx, npos * H * D), 256, 0, ctx->stream>>>(src_phd, (__half*)dst_hpd, pos0, npos, n_ctx, H, D);
+    THK_LAUNCH_CHECK();
+    return THK_OK;
+}
+__global__ void kv_from_hpd_f16_kernel(const __half* __restrict__ src, float* __restrict__ dst, int64_t pos0, int64_t npos, int64_t n_ctx,
+                                       int64_t H, int64_t D) {
+    const int64_t total = npos * H * D;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = i % D, h = (i / D) % H, pz = i / (D * H);
+        dst[((pos0 + pz) * H + h) * D + d] = __half2float(src[(h * n_ctx + pos0 + pz) * D + d]);
+    }
+}
+extern "C" int thk_kv_from_hpd_f16(thk_ctx* ctx, const uint16_t* src_hpd, float* dst_phd, int64_t pos0, int64_t npos, int64_t n_ctx,
+                                   int64_t H, int64_t D) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx && src_hpd && dst_phd, "thk_kv_from_hpd_f16: null argument");
+    THK_CHECK_ARG(pos0 >= 0 && npos > 0 && pos0 + npos <= n_ctx && H > 0 && D > 0, "thk_kv_from_hpd_f16: bad range");
+    kv_from_hpd_f16_kernel<<<ew_blocks(ctx, npos * H * D), 256, 0, ctx->stream>>>((const __half*)src_hpd, dst_phd, pos0, npos, n_ctx, H, D);
+    THK_LAUNCH_CHECK();
+    return THK_OK;
+}
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = __float2half_rn(src[i]);
+}
+extern "C" int thk_f32_to_f16(thk_ctx* ctx, const float* src, uint16_t* dst, int64_t n) {
+    THK_ENTER(ctx);
+    THK_CHECK_ARG(ctx && src && dst && n > 0, "thk_f32_to_f16: bad argument");
+    f32_to_f16_kernel<<<ew_blocks(ctx, n), 256, 0, ctx->stream>>>(src, (__half*)dst, n);
+    THK_LAUNCH_CHECK();
+    return THK_OK;
+}
 // the inverse hand-over: rows [pos0, pos0+npos) of the fused decoder's [head][n_ctx][dim] cache back into the op graph's
 // [pos][head][dim] cache, so that a batched pass or the op graph can continue a context the fused kernel extended
 __global__ void kv_from_hpd_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t pos0, int64_t npos, int64_t n_ctx,

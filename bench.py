@@ -343,10 +343,10 @@ def main():
 
     peak, peak_src = load_peaks()
 
-    def roofline_of(ms, ctx, traffic=None):
+    def roofline_of(ms, ctx, traffic=None, kv_elem_bytes=4):
         # per-GPU algorithmic bytes: matrices and KV shard by tp; gains and the embedding row are replicated
         bytes_w = (args.layers * 2 * (4 * E * E + 3 * E * F) + 2 * V * E) // world + (2 * args.layers + 1) * 4 * E + 2 * E
-        bytes_total = bytes_w + kv_bytes(ctx, args.layers) // world
+        bytes_total = bytes_w + kv_bytes(ctx, args.layers) * kv_elem_bytes // 4 // world
         achieved = bytes_total / (ms * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": "decode_kernel (persistent, 1 launch per token per GPU)", "achieved": achieved, "per_gpu": True, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -383,6 +383,17 @@ def main():
         ms2 = timed_steps(m2, max(20, args.steps // 2), 2047)
         extra["ctx2048_decode"] = {"workload": workload_name(2048), "value": 1e3 / ms2, "unit": "tokens/s", "ms_per_step": ms2,
                                    "roofline": roofline_of(ms2, 2048)}
+        # the f16 KV option (parity budget in tests/test_gpu_kv_f16.py): the same step with half the KV bytes
+        m3 = th.LlamaModel.synthetic(dev, V, E, NMULT, H, L, 2048, kv_f16=True)
+        m3.fill_kv(2047)
+        m3.set_token(1)
+        for _ in range(5):
+            m3.step_async(2047)
+        ms3 = timed_steps(m3, max(20, args.steps // 2), 2047)
+        m3.close()
+        extra["ctx2048_decode_f16kv"] = {"workload": workload_name(2048) + ", f16 KV cache option (not the reference's f32 cache)",
+                                         "value": 1e3 / ms3, "unit": "tokens/s", "ms_per_step": ms3,
+                                         "roofline": roofline_of(ms3, 2048, kv_elem_bytes=2)}
         # configs[2]: a 128-token prompt in one batched pass (tcgen05 GEMM path) at n_past = 0, then one decode step
         prompt = (np.arange(128, dtype=np.int64) * 7919 % V).astype(np.int32).tolist()
         for _ in range(2):

@@ -34,7 +34,7 @@ def main(tag):
     m = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
     lines = [f"# ncu --set full: decode_kernel ({tag})", "",
              "Capture: `ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 4 -c 1` on "
-             "`bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e` (LLaMA-7B, ctx 512, 1xB200). Numbers printed by a run under "
+             "`bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extra --no-parity` (LLaMA-7B, ctx 512, 1xB200). Numbers printed by a run under "
              "ncu are never bench values; this file is evidence for traffic and pipe usage only.", "", "| metric | value | unit |", "|---|---|---|"]
     for k in KEYS:
         if k in m:
@@ -64,7 +64,7 @@ def main(tag):
     lines += ["Warp-stall samples by SASS opcode (top 12) and warp-level instructions executed:", "", "| opcode | samples % | executed |", "|---|---|---|"]
     for op, n in agg.most_common(12):
         lines.append(f"| {op} | {100*n/tot:.1f} | {ex[op]:,} |")
-    lines += ["", f"Total warp instructions: {sum(ex.values()):,}; useful (HADD2 cvt + FFMA): {ex['HADD2']+ex['FFMA']:,}.", ""]
+    lines += ["", f"Total warp instructions: {sum(ex.values()):,}; useful (HADD2.F32 converts + FFMA2 + FFMA): {ex['HADD2']+ex['FFMA2']+ex['FFMA']:,}; BRA / ISETP / BSYNC are mostly the spin loops of the waits.", ""]
     open(os.path.join(out_dir, f"{tag}_decode_kernel_ncu.md"), "w").write("\n".join(lines))
     json.dump({"tag": tag, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "algorithmic_bytes": alg,
                "kernel_ms_under_ncu": float(m["gpu__time_duration.sum"][0])}, open(os.path.join(out_dir, "decode_kernel_traffic.json"), "w"), indent=1)
@@ -86,7 +86,7 @@ def main(tag):
             by[name][1] += t
         total = sum(v[1] for v in by.values())
         ll = [f"# ncu launch list ({tag})", "",
-              "`ncu --metrics gpu__time_duration.sum --clock-control none -c 2000` on `bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e`.",
+              "`ncu --metrics gpu__time_duration.sum --clock-control none -c 2000` on `bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-extra --no-parity`.",
               "Includes model construction (synthetic weight fill kernels) -- per-launch times are cold-cache and serialised; compare shares.", "",
               "| kernel | launches | total ms | share % | avg us |", "|---|---|---|---|---|"]
         for k, (n, t) in sorted(by.items(), key=lambda kv: -kv[1][1]):

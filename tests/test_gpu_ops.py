@@ -149,6 +149,27 @@ def test_attention_ops_chain(dev, K, oracle):
     assert np.abs(do.numpy() - o_ref).max() < 1e-5
 
 
+@pytest.mark.parametrize("B,M,Kd,N", [(3, 20, 33, 70), (32, 128, 128, 128), (2, 64, 16, 64), (1, 8, 200, 5), (4, 130, 64, 129)])
+@pytest.mark.parametrize("transposeB", [1, 0])
+@pytest.mark.parametrize("use_uniforms", [False, True])
+def test_mat_mul_f32_tiled_batch_path(dev, K, oracle, B, M, Kd, N, transposeB, use_uniforms):
+    """the attention matmuls of a batched prompt pass (M >= 8, f32 B): 64 x 64 tiled kernel, ragged edges in every dimension"""
+    import token_hawk_b200 as t
+    r = rng(B * 1000 + M + N + Kd)
+    A = r.standard_normal((B, M, Kd)).astype(np.float32)
+    Bm = r.standard_normal((B, N, Kd) if transposeB else (B, Kd, N)).astype(np.float32)
+    dA, dB = dev.array(A), dev.array(Bm)
+    dC = dev.array(np.full((B, M, N), np.nan, np.float32))
+    scale = 0.125 if use_uniforms else None
+    u = t.device_struct(dev, t.DimsUniforms(A_B=B, A_M=M, A_N=Kd, scale=0.125, B_B=B, B_M=Kd, B_N=N)) if use_uniforms else None
+    _ok(K.thk_mat_mul(dev.h, dA.ptr, dB.ptr, dC.ptr, B, M, Kd, N, transposeB, 0, u.ptr if u else None), K)
+    ref = oracle.mat_mul(A, Bm, bool(transposeB), scale=scale)
+    got = dC.numpy()
+    bound = np.abs(A).astype(np.float64) @ (np.abs(Bm).astype(np.float64).transpose(0, 2, 1) if transposeB else np.abs(Bm).astype(np.float64))
+    assert np.isfinite(got).all()
+    assert (np.abs(got - ref) <= 2e-6 * bound * (0.125 if use_uniforms else 1.0) + 1e-7).all()
+
+
 def test_mat_mul_f16_weights_batch_path(dev, K, oracle):
     r = rng(11)
     M, Kd, N = 8, 512, 96

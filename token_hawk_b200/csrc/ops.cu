@@ -260,6 +260,72 @@ __global__ void __launch_bounds__(128) mat_mul_nn_kernel(const float* __restrict
         Cm[o] = do_scale ? acc * scale : acc;
     }
 }
+// f32 x f32 with more than a few rows of A (the attention matmuls of a batched prompt pass: [H][T][D] x [H][N][D]^T and
+// [H][T][N] x [H][N][D]): 64 x 64 output tile per CTA, K in steps of 16 through shared memory, 4 x 4 outputs per thread.
+// (The per-output-warp kernels above took 142 + 41 us per layer at T = 128 -- a quarter of the 128-token prefill,
+// profiles/v7_prefill_launches.md; they remain for M == 1 and for f16 B.)
+template <bool TB>
+__global__ void __launch_bounds__(256) mat_mul_tiled_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ Cm,
+                                                            int64_t batch, int64_t M, int64_t K, int64_t N,
+                                                            const thk_dims_uniforms* __restrict__ u) {
+    float scale = 1.0f;
+    bool do_scale = false;
+    if (u) { M = u->A_M; N = u->B_N; K = u->A_N; scale = u->scale; do_scale = true; }
+    __shared__ float As[16][65], Bs[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t tiles_m = (M + 63) / 64, tiles_n = (N + 63) / 64;
+    for (int64_t t = blockIdx.x; t < batch * tiles_m * tiles_n; t += gridDim.x) {
+        const int64_t z = t / (tiles_m * tiles_n), rem = t % (tiles_m * tiles_n);
+        const int64_t m0 = (rem / tiles_n) * 64, n0 = (rem % tiles_n) * 64;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int64_t k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = (int)threadIdx.x + i * 256;
+                {
+                    const int r = idx >> 4, kk = idx & 15;
+                    const int64_t m = m0 + r, k = k0 + kk;
+                    As[kk][r] = (m < M && k < K) ? A[(z * M + m) * K + k] : 0.f;
+                }
+                if (TB) {
+                    const int c = idx >> 4, kk = idx & 15;
+                    const int64_t n = n0 + c, k = k0 + kk;
+                    Bs[kk][c] = (n < N && k < K) ? Bm[(z * N + n) * K + k] : 0.f;
+                } else {
+                    const int kk = idx >> 6, c = idx & 63;
+                    const int64_t n = n0 + c, k = k0 + kk;
+                    Bs[kk][c] = (n < N && k < K) ? Bm[(z * K + k) * N + n] : 0.f;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                float a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty + 16 * i]; b[i] = Bs[kk][tx + 16 * i]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t m = m0 + ty + 16 * i;
+            if (m >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t n = n0 + tx + 16 * j;
+                if (n < N) Cm[(z * M + m) * N + n] = do_scale ? acc[i][j] * scale : acc[i][j];
+            }
+        }
+    }
+}
 extern "C" int thk_mat_mul(thk_ctx* ctx, const float* A, const void* B, float* C, int64_t batch, int64_t M, int64_t K,
                            int64_t N, int transposeB, int b_is_f16, const thk_dims_uniforms* uniforms) {
     THK_ENTER(ctx);
@@ -267,7 +333,12 @@ extern "C" int thk_mat_mul(thk_ctx* ctx, const float* A, const void* B, float* C
     if (batch <= 0) batch = 1;
     THK_CHECK_ARG(M > 0 && K > 0 && N > 0, "thk_mat_mul: one of the dimensions is zero");
     const int64_t total = batch * M * N;
-    if (transposeB) {
+    // NOTE: with uniforms the kernels take M, N, K from the device; the host values only size the grid
+    if (!b_is_f16 && M >= 8) {
+        int64_t blocks = batch * ((M + 63) / 64) * ((N + 63) / 64); const int64_t cap = (int64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
+        if (transposeB) mat_mul_tiled_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(A, (const float*)B, C, batch, M, K, N, uniforms);
+        else mat_mul_tiled_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(A, (const float*)B, C, batch, M, K, N, uniforms);
+    } else if (transposeB) {
         int64_t blocks = (total + 7) / 8; const int64_t cap = (int64_t)ctx->sm_count * 8; if (blocks > cap) blocks = cap;
         if (b_is_f16) mat_mul_tb_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(A, B, C, batch, M, K, N, 0, uniforms);
         else mat_mul_tb_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(A, B, C, batch, M, K, N, 0, uniforms);

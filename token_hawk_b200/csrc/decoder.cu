@@ -91,6 +91,10 @@ struct DecParams {
     // expected epoch sees the value.  xf: residual stream entering a layer (epoch flag_epoch + l), h1f: after attention
     // (flag_epoch + l + 1), fff: FFN hidden (flag_epoch + l + 1).
     unsigned long long *h1f, *fff, *xf;
+    // att_flagged: q and the token's own K / V row also travel as epoch-stamped values, and the attention phase polls the
+    // 3 x head_dim values of its head instead of waiting for the grid barrier behind the QKV phase
+    unsigned long long *qf, *knf, *vnf;
+    int att_flagged;
     unsigned flag_epoch;
     int nosync;                         // DEBUG (wrong results): skip every cross-CTA wait, to time the pipeline without synchronisation
     int poll_single;                    // flagged reads: after a stale read spin on the one stale element before re-reading all
@@ -839,6 +843,20 @@ __device__ __forceinline__ float wait_flagged1(const DecParams& p, const unsigne
     return __uint_as_float((unsigned)w);
 }
 
+// four consecutive flagged elements (32-byte aligned), polled until all carry `epoch`
+__device__ __forceinline__ float4 wait_flagged4(const DecParams& p, const unsigned long long* ptr, unsigned epoch, bool& dead) {
+    unsigned long long e0, e1, e2, e3, t0 = 0;
+    unsigned it = 0;
+    while (true) {
+        ld_flagged2(ptr, e0, e1);
+        ld_flagged2(ptr + 2, e2, e3);
+        const bool ok = (unsigned)(e0 >> 32) == epoch && (unsigned)(e1 >> 32) == epoch && (unsigned)(e2 >> 32) == epoch && (unsigned)(e3 >> 32) == epoch;
+        if (ok || dead || p.nosync) break;
+        if ((++it & 63u) == 0u && poll_watchdog(p.status, p.timeout_ns, t0, 0x502u, 0u, epoch)) { dead = true; break; }
+    }
+    return make_float4(__uint_as_float((unsigned)e0), __uint_as_float((unsigned)e1), __uint_as_float((unsigned)e2), __uint_as_float((unsigned)e3));
+}
+
 // Single-query attention over this CTA's (head, KV split) units (cmdbuf_mat_mul QK^T * 1/sqrt(D),
 // cmdbuf_row_softmax, cmdbuf_mat_mul P*V; th-llama.cpp:365-380).  Every warp runs its own online
 // softmax over the positions j = warp (mod 8) of each K/V tile pair -- no CTA barrier per tile -- and
@@ -876,7 +894,15 @@ __device__ __forceinline__ unsigned long long math_att_phase(const DecParams& p,
         const int pb = min(pb_full, p.n_past);
         const bool has_new = (pb_full == a.N);
         float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act) {
+        if (act && p.att_flagged) {
+            // no grid barrier behind the QKV phase: the read of this head's q (and K / V row) is the wait
+            const unsigned epoch = p.flag_epoch + (unsigned)layer + 1u;
+            q4 = wait_flagged4(p, p.qf + h * D + (lane << 2), epoch, c.dead);
+            if (has_new && mw == 0) {
+                *(float4*)(sc_kn + (lane << 2)) = wait_flagged4(p, p.knf + h * D + (lane << 2), epoch, c.dead);
+                *(float4*)(sc_vn + (lane << 2)) = wait_flagged4(p, p.vnf + h * D + (lane << 2), epoch, c.dead);
+            }
+        } else if (act) {
             q4 = __ldcg((const float4*)(p.q + h * D) + lane);
             if (has_new && mw == 0) {   // the token's own K/V row (QKV epilogue of this launch): same L2 round trip as q,
                 const size_t off = ((size_t)h * p.n_ctx + p.n_past) * D;     // parked in shared memory until the tiles are done
@@ -1179,7 +1205,7 @@ __device__ void math_main(const DecParams& p, int tok) {
         if (k == K_WO) prefetch_gain(L->ffn_norm, p.n_embd, ct);
         else if (k == K_W2) prefetch_gain(l + 1 < p.n_layer ? p.layers[l + 1].attention_norm : p.norm, p.n_embd, ct);
         mark(pm, p, (unsigned)i, PROF_ARRIVE);
-        if (k == K_QKV || k == K_ATT) {                  // (Wo -> W13 -> W2 -> QKV: the next prologue waits on the flagged vector itself)
+        if ((k == K_QKV && !p.att_flagged) || k == K_ATT) {   // (Wo -> W13 -> W2 -> QKV: the next prologue waits on the flagged vector itself)
             if (k == K_ATT) bar_sync(BAR_PRE, kMathThreads + 32);    // our global writes (split results) precede the epilogue warp's arrive
             bar_sync(BAR_ALL, kMathThreads + 32);                     // the epilogue warp has passed the grid barrier
         }
@@ -1289,14 +1315,21 @@ __device__ __forceinline__ void epi_mat_phase(const DecParams& p, const Smem& S,
                         const size_t idx = ((size_t)(r / D) * n_ctx + n_past) * D + (r % D);
                         if (!p.kv_f16) L->value_cache[idx] = y;
                         else ((__half*)L->value_cache)[idx] = __float2half_rn(y);
+                        if (p.att_flagged) st_flagged(p.vnf + r, p.kv_f16 ? __half2float(__float2half_rn(y)) : y, epoch);
                     } else if ((lane & 1) == 0) {                    // Q / K: rotate the pair (r, r+1), th.cpp:1457-1492
                         const float2 cs = S.misc->rope[(r % D) >> 1];
                         const float a = y * cs.x - y1 * cs.y, b = y * cs.y + y1 * cs.x;
-                        if (si == 0) { *(float2*)(p.q + r) = make_float2(a, b); }
-                        else {                                                                            // th-llama.cpp:337
+                        if (si == 0) {
+                            *(float2*)(p.q + r) = make_float2(a, b);
+                            if (p.att_flagged) { st_flagged(p.qf + r, a, epoch); st_flagged(p.qf + r + 1, b, epoch); }
+                        } else {                                                                          // th-llama.cpp:337
                             const size_t idx = ((size_t)(r / D) * n_ctx + n_past) * D + (r % D);
                             if (!p.kv_f16) *(float2*)(L->key_cache + idx) = make_float2(a, b);
                             else *(__half2*)((__half*)L->key_cache + idx) = __floats2half2_rn(a, b);
+                            if (p.att_flagged) {
+                                st_flagged(p.knf + r, p.kv_f16 ? __half2float(__float2half_rn(a)) : a, epoch);
+                                st_flagged(p.knf + r + 1, p.kv_f16 ? __half2float(__float2half_rn(b)) : b, epoch);
+                            }
                         }
                     }
                     break;
@@ -1351,7 +1384,7 @@ __device__ void epi_main(const DecParams& p, const Smem& S) {
             bar_sync(BAR_PRE, kMathThreads + 32);
         }
         if (k == K_OUT) break;
-        if (k == K_QKV || k == K_ATT) {
+        if ((k == K_QKV && !p.att_flagged) || k == K_ATT) {
             ++nbar;
             grid_barrier(p, nbar, lane, dead);
             bar_sync(BAR_ALL, kMathThreads + 32);
@@ -1612,10 +1645,11 @@ static int decoder_alloc(thk_decoder* d, const thk_llama_layer* layers) {
     float* f = d->scratch;
     p.x = f; f += p.n_embd; p.q = f; f += p.Eh;
     p.part = f; f += part_n; p.amax_val = f; f += d->grid; p.amax_idx = (int*)f;
-    const size_t nflag = (size_t)2 * p.n_embd + (size_t)((p.Fh + 1) & ~1);
+    const size_t nflag = (size_t)2 * p.n_embd + (size_t)((p.Fh + 1) & ~1) + (size_t)3 * p.Eh;
     THK_CUDA(cudaMalloc(&d->flagged, nflag * sizeof(unsigned long long)));
     THK_CUDA(cudaMemset(d->flagged, 0, nflag * sizeof(unsigned long long)));     // epoch 0 is never used
     p.h1f = d->flagged; p.xf = p.h1f + p.n_embd; p.fff = p.xf + p.n_embd;
+    p.qf = p.fff + ((p.Fh + 1) & ~1); p.knf = p.qf + p.Eh; p.vnf = p.knf + p.Eh;
     const size_t nctrl = 64 + 4;
     THK_CUDA(cudaMalloc(&d->ctrl, nctrl * sizeof(unsigned)));
     THK_CUDA(cudaMemset(d->ctrl, 0, nctrl * sizeof(unsigned)));
@@ -1673,6 +1707,7 @@ extern "C" int thk_decoder_create(thk_ctx* ctx, const thk_llama_dims* dims, cons
     // tuning knobs (defaults = the measured best)
     p.l2_ahead = (unsigned)(getenv("THK_L2_AHEAD_KB") ? atoi(getenv("THK_L2_AHEAD_KB")) : 64) * 1024u;
     p.poll_single = getenv("THK_POLL_SINGLE") ? atoi(getenv("THK_POLL_SINGLE")) : 2;
+    p.att_flagged = getenv("THK_ATT_FLAGGED") ? atoi(getenv("THK_ATT_FLAGGED")) : 0;
     const int max_vec = p.n_embd > p.Fh ? p.n_embd : p.Fh;
     d->smem = decode_smem_bytes(max_vec);
     if (d->smem > 227 * 1024) {
@@ -1763,6 +1798,7 @@ extern "C" int thk_decoder_tune(thk_decoder* d, const char* key, int value) {
     THK_CHECK_ARG(d && key, "thk_decoder_tune: null argument");
     if (!strcmp(key, "l2_ahead_kb")) { THK_CHECK_ARG(value >= 0 && value <= 1024, "l2_ahead_kb out of range"); d->p.l2_ahead = (unsigned)value * 1024u; }
     else if (!strcmp(key, "prof_phase")) d->p.prof_phase = value;
+    else if (!strcmp(key, "att_flagged")) d->p.att_flagged = value != 0;
     else if (!strcmp(key, "poll_single")) { THK_CHECK_ARG(value >= 0 && value <= 2, "poll_single: 0, 1 or 2"); d->p.poll_single = value; }
     else if (!strcmp(key, "nosync")) d->p.nosync = value != 0;
     else if (!strcmp(key, "timeout_ms")) { THK_CHECK_ARG(value > 0, "timeout_ms must be positive"); d->p.timeout_ns = (unsigned long long)value * 1000000ull; }

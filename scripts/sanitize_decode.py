@@ -17,13 +17,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--n-past", type=int, default=0)
     ap.add_argument("--ctx", type=int, default=160)
+    ap.add_argument("--kv-f16", action="store_true", help="f16 KV cache option of the fused path")
     args = ap.parse_args()
     import token_hawk_b200 as th
     dev = th.Device(0)
     if args.tiny:
-        m = th.LlamaModel.synthetic(dev, 512, 512, 256, 8, 2, 64)
+        m = th.LlamaModel.synthetic(dev, 512, 512, 256, 8, 2, 64, kv_f16=args.kv_f16)
     else:
-        m = th.LlamaModel.synthetic(dev, 32000, 4096, 256, 32, args.layers, args.ctx)
+        m = th.LlamaModel.synthetic(dev, 32000, 4096, 256, 32, args.layers, args.ctx, kv_f16=args.kv_f16)
     if args.n_past:
         m.fill_kv(args.n_past)
     tok = 1

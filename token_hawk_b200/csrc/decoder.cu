@@ -731,10 +731,12 @@ __device__ __forceinline__ unsigned long long math_mat_phase(const DecParams& p,
                     if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
                     const uint32_t eb = S.empty_a + c.ring.sl * 8;
                     c.ring.advance();
+#ifndef THK_EXP_NOMATH      // (measurement build, wrong results: tiles are waited for and released, not multiplied)
                     TileW t;
                     tile_ldw(wa, stride, t);
 #pragma unroll
                     for (int r = 0; r < kRows; ++r) fma8(t.w[r], xr[kt], acc[r]);
+#endif
                     __syncwarp();                                 // every lane has read the tile (lanes may have diverged at the waits)
                     if (lane == 0) mbar_arrive(eb);
                     if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
@@ -752,12 +754,14 @@ __device__ __forceinline__ unsigned long long math_mat_phase(const DecParams& p,
                 if (first) { mark(pm, p, phase_idx, PROF_FIRST_TILE); first = false; }
                 const uint32_t eb = S.empty_a + c.ring.sl * 8;
                 c.ring.advance();
+#ifndef THK_EXP_NOMATH
                 TileW t;
                 unsigned long long xp[4];
                 xs_ld(ok ? xlane_a + ((uint32_t)col0 << 2) : S.xs_a + ((uint32_t)lane << 4), ok, xp);
                 tile_ldw(wa, stride, t);
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) fma8(t.w[r], xp, acc[r]);
+#endif
                 __syncwarp();
                 if (lane == 0) mbar_arrive(eb);
                 if (pm != nullptr && (int)phase_idx == p.prof_phase && ntile < kProfTiles) prof_tile(PROF(p), 0, ntile++);
@@ -1179,17 +1183,24 @@ __device__ void math_main(const DecParams& p, int tok) {
         // ---- prologue ----
         const unsigned epoch = p.flag_epoch + (unsigned)l + 1u;          // flagged vectors written in layer l (K_QKV / K_OUT read layer l-1's x)
         const long long tp0 = wstat_t0();
+#ifdef THK_EXP_NOPRO      // measurement build (wrong results): no prologue, profiles/r2_timeline_and_experiments.md section 1
+        if (i == 0) {
+#else
         if (k == K_QKV || k == K_W13 || k == K_OUT) {
+#endif
             const float* gain = (k == K_QKV) ? L->attention_norm : (k == K_W13) ? L->ffn_norm : p.norm;
             // step 0: x <- f32(tok_embeddings[token]) (th-llama.cpp:577-585; device-side like :552-575): every CTA converts
             // the row itself and publishes its share as the flagged residual stream (the Wo epilogue / the reducer adds to it)
             const unsigned long long* fsrc = i == 0 ? nullptr : (k == K_W13 ? p.h1f : p.xf);
             ss = prologue_norm(p, phase_of(k), emb_row, fsrc, k == K_W13 ? epoch : epoch - 1u, gain, i == 0 ? p.xf : nullptr);
-        } else if (k == K_WO) {
+        }
+#ifndef THK_EXP_NOPRO
+        else if (k == K_WO) {
             prologue_att_merge(p, PH_WO);
         } else if (k == K_W2) {
             prologue_copy(p, PH_W2, p.fff, epoch);
         }
+#endif
         wstat_add(WS_POLL, tp0);
         // ---- tiles ----
         if (k == K_ATT) {

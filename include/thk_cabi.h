@@ -217,10 +217,11 @@ int thk_decoder_set_peers(thk_decoder* dec, void* const* peer_bufs, void* const*
 /* ---- batched-prompt path (tensor cores): Y[M,N] = X[M,K] * W[N,K]^T, W f16, X/Y f32 ----
  * replaces cmdbuf_mat_mul with an f16 B operand on the n_tokens > 1 path (th-llama.cpp:308-310,
  * 404, 429-430, 444). tcgen05 + TMEM + TMA; X is split into f16 hi + lo terms so the result keeps
- * f32-activation accuracy. */
+ * f32-activation accuracy.  N % 32 == 0 and K % 64 == 0; N % 128 == 0 (every LLaMA matrix) takes 128 x 128 tiles with
+ * split-K over ~one CTA per SM, the K slices added in slice order (deterministic).  Launches on the context's stream. */
 int thk_gemm_f16_tc(thk_ctx* ctx, const float* X, const uint16_t* W, float* Y, int64_t M, int64_t N, int64_t K);
-/* sizes the context's hi/lo workspace for X up to [max_M, max_K] once (post_load_init_model allocates all working buffers
- * at load time, th-llama-loader.cpp:330-435), so that thk_gemm_f16_tc itself never allocates */
+/* sizes the context's workspace (hi/lo panels of X up to [max_M, max_K] + split-K partial tiles) once (post_load_init_model
+ * allocates all working buffers at load time, th-llama-loader.cpp:330-435), so that thk_gemm_f16_tc itself never allocates */
 int thk_gemm_reserve(thk_ctx* ctx, int64_t max_M, int64_t max_K);
 /* blocks on the stream; THK_E_TIMEOUT if a GEMM launch hit its in-kernel watchdog */
 int thk_gemm_check(thk_ctx* ctx);

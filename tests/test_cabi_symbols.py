@@ -61,6 +61,12 @@ def test_kernels_are_sm100a_native(built):
     dec = sass[sass.index("decode_kernelILb0"):]
     dec = dec[:dec.index("Function :", 20)] if "Function :" in dec[20:] else dec
     assert "UBLKCP" in dec and "UBLKPF" in dec and "FFMA2" in dec and "SYNCS" in dec and "HMMA" not in dec
+    # setmaxnreg both ways, and NO local-memory access in the math warps' code (everything after the register
+    # re-allocation upwards): a spill there is an L2 access behind the weight stream and costs up to 1.2 ms/token
+    # (profiles/r2_timeline_and_experiments.md section 2)
+    assert "USETMAXREG.DEALLOC" in dec and "USETMAXREG.TRY_ALLOC" in dec
+    math_code = dec[dec.index("USETMAXREG.TRY_ALLOC"):]
+    assert " STL" not in math_code and " LDL" not in math_code, "register spill in the math warps of decode_kernel"
     assert "UTCHMMA" in sass or "UTCQMMA" in sass or "UTCMMA" in sass, "tcgen05 MMA missing from the prefill GEMM"
     assert "UTMALDG" in sass, "TMA tensor loads missing from the prefill GEMM"
 

@@ -60,6 +60,10 @@ constexpr int kServiceRegs = 72, kMathRegs = 216;
 constexpr int kRows = 8;                              // rows per row group (= per tile)
 constexpr int kMaxTilePos = 128;                      // attention: positions per tile cap
 constexpr int kMaxHeadDim = 128;
+#ifndef THK_ATT_PER_ROUND
+#define THK_ATT_PER_ROUND 4
+#endif
+constexpr int kAttPerRound = THK_ATT_PER_ROUND;       // attention: positions a warp scores per round (8 would halve the rounds of a 64-position tile but spills in the math warps: ptxas, not measured)
 constexpr int kMaxSplit = 8;                          // attention: KV splits per head cap
 #ifndef THK_COPY_CHUNKS
 #define THK_COPY_CHUNKS 3
@@ -937,27 +941,27 @@ __device__ __forceinline__ unsigned long long math_att_phase(const DecParams& p,
             wait_full(p, S, cv, 5);
             const void* vt = (const void*)(S.slots + cv.ring.sl * kSlotBytes);
             c.dead = c.dead || cv.dead;
-            for (int j0 = mw; j0 < np; j0 += 4 * kMathWarps) {      // 4 positions of this warp per round
-                float s[4];
+            for (int j0 = mw; j0 < np; j0 += kAttPerRound * kMathWarps) {      // kAttPerRound positions of this warp per round
+                float s[kAttPerRound];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
+                for (int t = 0; t < kAttPerRound; ++t) {
                     const int j = j0 + t * kMathWarps;
                     s[t] = (act && j < np) ? dot4(q4, kv_row4(kt, j, D, lane, kvh)) : 0.f;
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], off);
+                    for (int t = 0; t < kAttPerRound; ++t) s[t] += __shfl_xor_sync(0xffffffffu, s[t], off);
                 }
                 float mx = -INFINITY;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) { s[t] = (j0 + t * kMathWarps < np) ? s[t] * scale : -INFINITY; mx = fmaxf(mx, s[t]); }
+                for (int t = 0; t < kAttPerRound; ++t) { s[t] = (j0 + t * kMathWarps < np) ? s[t] * scale : -INFINITY; mx = fmaxf(mx, s[t]); }
                 const float m_new = fmaxf(m, mx);
                 const float corr = expf(m - m_new);
                 lsum *= corr; o4.x *= corr; o4.y *= corr; o4.z *= corr; o4.w *= corr;
                 m = m_new;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
+                for (int t = 0; t < kAttPerRound; ++t) {
                     const int j = j0 + t * kMathWarps;
                     if (j < np) {
                         const float pj = expf(s[t] - m);
